@@ -1,0 +1,187 @@
+"""warp_rnnt_b200 -- B200-native RNN-Transducer loss, drop-in for 1ytic/warp-rnnt's
+``warp_rnnt.rnnt_loss`` (reference: /root/reference/pytorch_binding/warp_rnnt/__init__.py).
+
+Same public surface as the reference module (``__init__.py:9-143``):
+
+    rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=False,
+              reduction='none', blank=0, gather=False, fastemit_lambda=0.0, compact=False)
+    RNNTLoss, RNNTLossCompact (autograd Functions), __version__, and the operator module ``_C``
+    (rnnt_loss / rnnt_loss_compact / rnnt_loss_compact_backward, same kwargs and error strings).
+
+Host code here is plumbing only (argument handling, autograd wiring); all arithmetic runs in the
+hand-written sm_100a kernels of ``lib/librnnt_b200.so`` through ``lib/_C.so``.  There is no CPU or
+eager-PyTorch fallback: importing this package without the built extension raises ImportError.
+"""
+import importlib.machinery
+import importlib.util
+import os
+import sys
+
+import torch
+
+__version__ = "0.1.0"
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_EXT_PATH = os.path.join(_HERE, "lib", "_C.so")
+_LIB_PATH = os.path.join(_HERE, "lib", "librnnt_b200.so")
+
+
+def _load_ext():
+    if not (os.path.exists(_EXT_PATH) and os.path.exists(_LIB_PATH)):
+        if os.environ.get("RNNT_B200_NO_AUTOBUILD") == "1":
+            raise ImportError(
+                "warp_rnnt_b200: the CUDA extension is not built (%s missing). "
+                "Run `python -m warp_rnnt_b200.build`; there is no CPU fallback." % _EXT_PATH)
+        from . import build as _build        # builds the CUDA extension itself (nvcc + g++)
+        _build.build_all()
+    name = __name__ + "._C"
+    loader = importlib.machinery.ExtensionFileLoader(name, _EXT_PATH)
+    spec = importlib.util.spec_from_file_location(name, _EXT_PATH, loader=loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    sys.modules[name] = mod
+    return mod
+
+
+_C = _load_ext()
+core = _C
+
+LSE_AUTO, LSE_EXACT, LSE_FAST = 0, 1, 2
+
+
+def set_lse_mode(mode):
+    """'auto' | 'exact' | 'fast' (see include/rnnt_b200.h rnntLseMode_t).  'exact' reproduces the
+    reference kernels' alpha/beta/cost/gradient bits; 'fast' shortens the wavefront's dependent chain."""
+    _C.set_lse_mode({"auto": 0, "exact": 1, "fast": 2}[mode] if isinstance(mode, str) else int(mode))
+
+
+class RNNTLoss(torch.autograd.Function):
+    """Dense / gathered-input loss.  Reference: ``RNNTLoss`` (__init__.py:9-24).
+
+    The reference materialises the dense gradient in forward and multiplies it in place by
+    grad_output in backward (two more dense passes).  Here forward keeps the gradient in its
+    (N,T,U,2) [blank,label] form and backward emits the dense (N,T,U,V) tensor once, already
+    scaled by grad_output -- one dense write in total.  With ``blank == -1`` the input is the
+    gathered (N,T,U,2) layout of the reference's operator boundary (binding.cpp:81-90)."""
+
+    @staticmethod
+    def forward(ctx, log_probs, labels, frames_lengths, labels_lengths, blank=0, fastemit_lambda=0.0,
+                accumulate=False):
+        need = ctx.needs_input_grad[0]
+        ctx.pairs_in = (blank == -1)
+        if ctx.pairs_in:
+            costs, grads = _C.rnnt_loss_dense(log_probs, labels, frames_lengths, labels_lengths, -1,
+                                              fastemit_lambda, None, need, 0)
+            ctx.grads = grads if need else None
+        else:
+            costs, pg = _C.rnnt_gather_forward(log_probs, labels, frames_lengths, labels_lengths, blank,
+                                               fastemit_lambda, need, 0)
+            ctx.grads = pg if need else None
+            ctx.labels = labels
+            ctx.V = log_probs.size(3)
+            ctx.blank = blank
+            ctx.accumulate = accumulate
+        return costs
+
+    @staticmethod
+    def backward(ctx, grads_output):
+        if ctx.grads is None:
+            return None, None, None, None, None, None, None
+        go = grads_output.contiguous().to(ctx.grads.dtype)
+        if ctx.pairs_in:
+            return ctx.grads * go.view(-1, 1, 1, 1), None, None, None, None, None, None
+        g = _C.rnnt_gather_backward(ctx.grads, ctx.labels, go, ctx.V, ctx.blank, ctx.accumulate)
+        return g, None, None, None, None, None, None
+
+
+class RNNTLossEager(torch.autograd.Function):
+    """Reference-shaped variant: dense gradients are produced in forward (one fused pass) and
+    scaled in backward, exactly like the reference's RNNTLoss (__init__.py:11-24)."""
+
+    @staticmethod
+    def forward(ctx, log_probs, labels, frames_lengths, labels_lengths, blank=0, fastemit_lambda=0.0):
+        costs, ctx.grads = _C.rnnt_loss(xs=log_probs, ys=labels, xn=frames_lengths, yn=labels_lengths,
+                                        blank=blank, fastemit_lambda=fastemit_lambda)
+        return costs
+
+    @staticmethod
+    def backward(ctx, grads_output):
+        grads_output = grads_output.view(-1, 1, 1, 1).to(ctx.grads)
+        return ctx.grads.mul_(grads_output), None, None, None, None, None
+
+
+class RNNTLossCompact(torch.autograd.Function):
+    """Compact (ragged) layout.  Reference: ``RNNTLossCompact`` (__init__.py:26-54)."""
+
+    @staticmethod
+    def forward(ctx, log_probs, labels, frames_lengths, labels_lengths, blank=0, fastemit_lambda=0.0,
+                enable_grad: bool = True):
+        costs, grads, loc = _C.rnnt_loss_compact(
+            xs=log_probs, ys=labels, xn=frames_lengths, yn=labels_lengths, blank=blank,
+            fastemit_lambda=fastemit_lambda, required_grad=enable_grad)
+        if enable_grad:
+            cumlen = torch.cumsum(frames_lengths * (labels_lengths + 1), dim=0, dtype=torch.int32)
+            ctx.V = log_probs.size(-1)
+            ctx.blank = blank
+            ctx.save_for_backward(grads, loc, cumlen)
+        return costs
+
+    @staticmethod
+    def backward(ctx, grads_output):
+        grads, loc, cumlen = ctx.saved_tensors
+        grads_input = _C.rnnt_loss_compact_backward(grads_output.contiguous().float(), grads, cumlen, loc,
+                                                    ctx.V, ctx.blank)
+        return grads_input, None, None, None, None, None, None
+
+
+def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=False, reduction="none",
+              blank=0, gather=False, fastemit_lambda=0.0, compact=False):
+    """The RNN-Transducer loss (same signature and semantics as the reference, __init__.py:57-143).
+
+    Args:
+        log_probs: (N, T, U, V) float32 log-softmaxed joint output; compact: (STU, V).
+        labels: (N, U-1) int32; compact: (sum(labels_lengths),).
+        frames_lengths, labels_lengths: (N,) int32.
+        average_frames: divide each sample's loss by its number of frames.
+        reduction: 'none' | 'mean' | 'sum' | None.
+        blank: blank label id.
+        gather: the reference's memory-saving mode.  Here both settings keep only a (N,T,U,2)
+            gradient between forward and backward; ``gather=True`` additionally follows
+            torch.gather's backward for a label equal to ``blank`` (the two gradients add).
+        fastemit_lambda: FastEmit regularisation (scales label gradients by 1+lambda).
+        compact: ragged layout, STU = sum(frames_lengths * (labels_lengths + 1)).
+    """
+    assert average_frames is None or isinstance(average_frames, bool)
+    assert reduction is None or reduction in ("none", "mean", "sum")
+    assert isinstance(blank, int)
+    assert isinstance(gather, bool)
+
+    assert not labels.requires_grad, "labels does not require gradients"
+    assert not frames_lengths.requires_grad, "frames_lengths does not require gradients"
+    assert not labels_lengths.requires_grad, "labels_lengths does not require gradients"
+
+    if compact:
+        costs = RNNTLossCompact.apply(log_probs.float(), labels, frames_lengths, labels_lengths, blank,
+                                      fastemit_lambda,
+                                      (log_probs.requires_grad and torch.is_grad_enabled()))
+    else:
+        # gather=True and gather=False share the fused path: the log-prob gather happens inside
+        # the forward kernels, the dense scatter inside the backward kernel.
+        costs = RNNTLoss.apply(log_probs, labels, frames_lengths, labels_lengths, blank, fastemit_lambda, gather)
+
+    if average_frames:
+        costs = costs / frames_lengths.to(log_probs)
+
+    if reduction == "none" or reduction is None:
+        return costs
+    elif reduction == "sum":
+        return costs.sum()
+    elif reduction == "mean":
+        return costs.mean()
+    else:
+        raise ValueError(
+            f"Unknown reduction method: {reduction}, expected to be one of ['mean', 'sum', 'none']")
+
+
+__all__ = ["rnnt_loss", "RNNTLoss", "RNNTLossEager", "RNNTLossCompact", "set_lse_mode", "core", "_C",
+           "__version__"]

@@ -1,0 +1,382 @@
+// api.cu -- the extern "C" surface of librnnt_b200.so (declared in include/rnnt_b200.h).
+//
+// (A) rnnt_b200_*: native interface bound by csrc/binding.cpp.
+// (B) run_warp_rnnt & co: the reference's C ABI (/root/reference/core.h:29-60) implemented on top
+//     of (A)'s kernels so the reference's own bindings link against this library unchanged.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace rnnt {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static int env_lse_mode() {
+    const char *e = getenv("RNNT_B200_LSE");
+    if (!e) return RNNT_LSE_AUTO;
+    if (!strcmp(e, "exact")) return RNNT_LSE_EXACT;
+    if (!strcmp(e, "fast")) return RNNT_LSE_FAST;
+    return RNNT_LSE_AUTO;
+}
+static std::atomic<int> g_lse_mode{-1};
+
+static int default_lse_mode() {
+    int m = g_lse_mode.load(std::memory_order_relaxed);
+    if (m < 0) {
+        m = env_lse_mode();
+        g_lse_mode.store(m, std::memory_order_relaxed);
+    }
+    return m;
+}
+
+// AUTO policy (DESIGN.md "numerics"): the exact chain is ~3x longer per anti-diagonal; it only
+// matters where the wavefront is exposed.  AUTO = fast; callers that want bit-parity with the
+// reference kernels ask for RNNT_LSE_EXACT (or set RNNT_B200_LSE=exact).
+static int resolve_kind(int lse_mode, bool compact) {
+    if (lse_mode == RNNT_LSE_AUTO) lse_mode = default_lse_mode();
+    if (lse_mode == RNNT_LSE_EXACT) return compact ? kExactCompact : kExactDense;
+    return kFast;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Workspace {
+    float2 *pairs;
+    float *alphas, *betas, *ll;
+    int *bad;
+    int64_t *mem_pref, *lab_pref;
+    int *totals;
+    size_t bytes;
+};
+
+static Workspace carve(void *base, int64_t cells, int N) {
+    Workspace w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void *p = base ? (void *)((char *)base + off) : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    const size_t c = (size_t)(cells > 0 ? cells : 0), n = (size_t)(N > 0 ? N : 0);
+    w.pairs = (float2 *)take(c * sizeof(float2));
+    w.alphas = (float *)take(c * sizeof(float));
+    w.betas = (float *)take(c * sizeof(float));
+    w.ll = (float *)take(2 * n * sizeof(float));
+    w.bad = (int *)take(n * sizeof(int));
+    w.mem_pref = (int64_t *)take(n * sizeof(int64_t));
+    w.lab_pref = (int64_t *)take(n * sizeof(int64_t));
+    w.totals = (int *)take(4 * sizeof(int));
+    w.bytes = off;
+    return w;
+}
+
+static bool dense_args_ok(int N, int T, int U, int V) {
+    if (N < 0 || T < 1 || U < 1 || V < 1) return false;
+    if ((int64_t)T * U >= (int64_t)1 << 31) return false;
+    if ((int64_t)N * T * U >= (int64_t)1 << 31) return false;   // cell ids are 32-bit in the emit kernel
+    if (V >= (1 << 22)) return false;
+    return true;
+}
+
+#define RNNT_TRY(expr, code)                                            \
+    do {                                                                \
+        cudaError_t e__ = (expr);                                       \
+        if (e__ != cudaSuccess) {                                       \
+            fprintf(stderr, "rnnt_b200: %s failed: %s\n", #expr, cudaGetErrorString(e__)); \
+            return (code);                                              \
+        }                                                               \
+    } while (0)
+
+}  // namespace rnnt
+
+using namespace rnnt;
+
+extern "C" {
+
+const char *rnnt_b200_version(void) { return "0.1.0 (sm_100a)"; }
+
+const char *rnnt_b200_status_string(int s) {
+    switch (s) {
+        case RNNT_STATUS_SUCCESS: return "success";
+        case RNNT_STATUS_WARP_FAILED: return "alpha/beta wavefront kernel failed";
+        case RNNT_STATUS_GRADS_BLANK_FAILED: return "gradient kernel failed";
+        case RNNT_STATUS_GRADS_LABEL_FAILED: return "gradient kernel (label) failed";
+        case RNNT_STATUS_COSTS_FAILED: return "cost kernel failed";
+        case RNNT_STATUS_INVALID_ARGUMENT: return "invalid argument";
+        case RNNT_STATUS_WORKSPACE_TOO_SMALL: return "workspace too small";
+        case RNNT_STATUS_GATHER_FAILED: return "gather kernel failed";
+        default: return "unknown status";
+    }
+}
+
+void rnnt_b200_set_lse_mode(int mode) {
+    if (mode < RNNT_LSE_AUTO || mode > RNNT_LSE_FAST) mode = RNNT_LSE_AUTO;
+    g_lse_mode.store(mode, std::memory_order_relaxed);
+}
+int rnnt_b200_get_lse_mode(void) { return default_lse_mode(); }
+
+uint64_t rnnt_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t rnnt_b200_workspace_bytes(int64_t cells, int N) { return carve(nullptr, cells, N).bytes; }
+
+int rnnt_b200_loss_dense(void *stream, void *workspace, size_t workspace_bytes, const float *log_probs,
+                         const int *labels, const int *xn, const int *yn, float *costs, float *grads,
+                         const float *grad_scale, int N, int T, int U, int V, int blank, float fastemit_lambda,
+                         int lse_mode) {
+    if (!dense_args_ok(N, T, U, V) || blank < 0 || blank >= V) return RNNT_STATUS_INVALID_ARGUMENT;
+    if (N == 0) return RNNT_STATUS_SUCCESS;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t cells = (int64_t)N * T * U;
+    const Workspace w = carve(workspace, cells, N);
+    if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
+    Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
+    RNNT_TRY(launch_gather(s, p, log_probs, labels, V, blank, w.pairs, nullptr, cells), RNNT_STATUS_GATHER_FAILED);
+    RNNT_TRY(launch_wavefront(s, resolve_kind(lse_mode, false), p, w.pairs, w.alphas, w.betas, w.ll, w.bad, costs,
+                              grads == nullptr, 1, U),
+             RNNT_STATUS_WARP_FAILED);
+    if (grads) {
+        ExpandSrc src = {};
+        src.pairs = w.pairs; src.alphas = w.alphas; src.betas = w.betas; src.bad = w.bad;
+        src.scale = grad_scale; src.labels = labels; src.fastemit_lambda = fastemit_lambda;
+        RNNT_TRY(launch_expand(s, p, src, grads, cells, V, blank), RNNT_STATUS_GRADS_BLANK_FAILED);
+    }
+    return RNNT_STATUS_SUCCESS;
+}
+
+int rnnt_b200_loss_pairs(void *stream, void *workspace, size_t workspace_bytes, const float *pairs, const int *xn,
+                         const int *yn, float *costs, float *pair_grads, int N, int T, int U,
+                         float fastemit_lambda, int lse_mode) {
+    if (!dense_args_ok(N, T, U, 2)) return RNNT_STATUS_INVALID_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(pairs) & 7u) || (reinterpret_cast<uintptr_t>(pair_grads) & 7u))
+        return RNNT_STATUS_INVALID_ARGUMENT;
+    if (N == 0) return RNNT_STATUS_SUCCESS;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t cells = (int64_t)N * T * U;
+    const Workspace w = carve(workspace, cells, N);
+    if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
+    Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
+    const float2 *pr = reinterpret_cast<const float2 *>(pairs);
+    RNNT_TRY(launch_wavefront(s, resolve_kind(lse_mode, false), p, pr, w.alphas, w.betas, w.ll, w.bad, costs,
+                              pair_grads == nullptr, 1, U),
+             RNNT_STATUS_WARP_FAILED);
+    if (pair_grads)
+        RNNT_TRY(launch_grads_pairs(s, p, pr, w.alphas, w.betas, w.bad, fastemit_lambda,
+                                    reinterpret_cast<float2 *>(pair_grads), cells),
+                 RNNT_STATUS_GRADS_BLANK_FAILED);
+    return RNNT_STATUS_SUCCESS;
+}
+
+int rnnt_b200_gather_forward(void *stream, void *workspace, size_t workspace_bytes, const float *log_probs,
+                             const int *labels, const int *xn, const int *yn, float *costs, float *pair_grads,
+                             int N, int T, int U, int V, int blank, float fastemit_lambda, int lse_mode) {
+    if (!dense_args_ok(N, T, U, V) || blank < 0 || blank >= V) return RNNT_STATUS_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(pair_grads) & 7u) return RNNT_STATUS_INVALID_ARGUMENT;
+    if (N == 0) return RNNT_STATUS_SUCCESS;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t cells = (int64_t)N * T * U;
+    const Workspace w = carve(workspace, cells, N);
+    if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
+    Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
+    RNNT_TRY(launch_gather(s, p, log_probs, labels, V, blank, w.pairs, nullptr, cells), RNNT_STATUS_GATHER_FAILED);
+    RNNT_TRY(launch_wavefront(s, resolve_kind(lse_mode, false), p, w.pairs, w.alphas, w.betas, w.ll, w.bad, costs,
+                              pair_grads == nullptr, 1, U),
+             RNNT_STATUS_WARP_FAILED);
+    if (pair_grads)
+        RNNT_TRY(launch_grads_pairs(s, p, w.pairs, w.alphas, w.betas, w.bad, fastemit_lambda,
+                                    reinterpret_cast<float2 *>(pair_grads), cells),
+                 RNNT_STATUS_GRADS_BLANK_FAILED);
+    return RNNT_STATUS_SUCCESS;
+}
+
+int rnnt_b200_gather_backward(void *stream, const float *pair_grads, const int *labels, const float *grad_out,
+                              float *out, int N, int T, int U, int V, int blank, int accumulate) {
+    if (!dense_args_ok(N, T, U, V) || blank < 0 || blank >= V) return RNNT_STATUS_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(pair_grads) & 7u) return RNNT_STATUS_INVALID_ARGUMENT;
+    if (N == 0) return RNNT_STATUS_SUCCESS;
+    Problem p = {nullptr, nullptr, nullptr, nullptr, N, T, U, 0};
+    ExpandSrc src = {};
+    src.pg = reinterpret_cast<const float2 *>(pair_grads);
+    src.scale = grad_out;
+    src.labels = labels;
+    src.label_adds = accumulate ? 1 : 0;
+    RNNT_TRY(launch_expand((cudaStream_t)stream, p, src, out, (int64_t)N * T * U, V, blank),
+             RNNT_STATUS_GRADS_BLANK_FAILED);
+    return RNNT_STATUS_SUCCESS;
+}
+
+int rnnt_b200_compact_forward(void *stream, void *workspace, size_t workspace_bytes, const float *xs, const int *ys,
+                              const int *xn, const int *yn, float *costs, float *pair_grads, int64_t *loc,
+                              int *totals, int64_t STU, int N, int V, int blank, float fastemit_lambda,
+                              int lse_mode) {
+    if (N < 0 || STU < 0 || V < 1 || V >= (1 << 22) || blank < 0 || blank >= V) return RNNT_STATUS_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(pair_grads) & 7u) return RNNT_STATUS_INVALID_ARGUMENT;
+    if (N == 0) return RNNT_STATUS_SUCCESS;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Workspace w = carve(workspace, STU, N);
+    if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
+    RNNT_TRY(launch_prefix(s, xn, yn, N, w.mem_pref, w.lab_pref, totals ? totals : w.totals), RNNT_STATUS_GATHER_FAILED);
+    Problem p = {xn, yn, w.mem_pref, w.lab_pref, N, 0, 0, 1};
+    RNNT_TRY(launch_gather(s, p, xs, ys, V, blank, w.pairs, loc, STU), RNNT_STATUS_GATHER_FAILED);
+    // no mismatch guard in the compact reference (core_compact.cu:347-358)
+    RNNT_TRY(launch_wavefront(s, resolve_kind(lse_mode, true), p, w.pairs, w.alphas, w.betas, w.ll, w.bad, costs,
+                              pair_grads == nullptr, 0, 512),
+             RNNT_STATUS_WARP_FAILED);
+    if (pair_grads)
+        RNNT_TRY(launch_grads_pairs(s, p, w.pairs, w.alphas, w.betas, nullptr, fastemit_lambda,
+                                    reinterpret_cast<float2 *>(pair_grads), STU),
+                 RNNT_STATUS_GRADS_BLANK_FAILED);
+    return RNNT_STATUS_SUCCESS;
+}
+
+int rnnt_b200_compact_totals(void *stream, const int *xn, const int *yn, int N, int64_t *scratch, int *totals) {
+    if (N <= 0 || !scratch || !totals) return RNNT_STATUS_INVALID_ARGUMENT;
+    RNNT_TRY(launch_prefix((cudaStream_t)stream, xn, yn, N, scratch, scratch + N, totals), RNNT_STATUS_GATHER_FAILED);
+    return RNNT_STATUS_SUCCESS;
+}
+
+int rnnt_b200_compact_backward(void *stream, const float *grad_cost, const float *pair_grads, const int64_t *loc,
+                               const int *cum_lens, float *out, int64_t STU, int N, int V, int blank) {
+    if (N < 0 || STU < 0 || V < 1 || V >= (1 << 22) || blank < 0 || blank >= V) return RNNT_STATUS_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(pair_grads) & 7u) return RNNT_STATUS_INVALID_ARGUMENT;
+    if (N == 0 || STU == 0) return RNNT_STATUS_SUCCESS;
+    Problem p = {nullptr, nullptr, nullptr, nullptr, N, 0, 0, 1};
+    ExpandSrc src = {};
+    src.pg = reinterpret_cast<const float2 *>(pair_grads);
+    src.scale = grad_cost;
+    src.loc = loc;
+    src.cum_lens = cum_lens;
+    RNNT_TRY(launch_expand((cudaStream_t)stream, p, src, out, STU, V, blank), RNNT_STATUS_GRADS_BLANK_FAILED);
+    return RNNT_STATUS_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------
+// (B) the reference's C ABI.  Scratch that the reference signatures have no room for comes
+// from the stream-ordered allocator (cudaMallocAsync / cudaFreeAsync on the same stream).
+// ------------------------------------------------------------------------------------------
+static void compat_die(const char *what, int status) {
+    // the reference's CHECK_KERNEL_STAT prints and exit(-1)s (core.h:7-14)
+    fprintf(stderr, "%s error: %s\n", what, rnnt_b200_status_string(status));
+    exit(-1);
+}
+
+int run_warp_rnnt(void *stream, unsigned int *counts, float *alphas, float *betas, const int *labels,
+                  const float *log_probs, float *grads, float *costs, const int *xn, const int *yn, int N, int T,
+                  int U, int V, int blank, float fastemit_lambda) {
+    (void)counts;
+    if (!dense_args_ok(N, T, U, V) || blank < 0 || blank >= V) return RNNT_STATUS_WARP_FAILED;
+    if (N == 0) return RNNT_STATUS_SUCCESS;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t cells = (int64_t)N * T * U;
+    const size_t pair_bytes = align_up((size_t)cells * sizeof(float2), 256);
+    const size_t small = align_up(sizeof(float) * 2 * N, 256) + align_up(sizeof(int) * N, 256);
+    char *tmp = nullptr;
+    if (cudaMallocAsync((void **)&tmp, pair_bytes + small, s) != cudaSuccess) return RNNT_STATUS_WARP_FAILED;
+    float2 *pairs = (float2 *)tmp;
+    float *ll = (float *)(tmp + pair_bytes);
+    int *bad = (int *)(tmp + pair_bytes + align_up(sizeof(float) * 2 * N, 256));
+    Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
+    int status = RNNT_STATUS_SUCCESS;
+    if (launch_gather(s, p, log_probs, labels, V, blank, pairs, nullptr, cells) != cudaSuccess)
+        status = RNNT_STATUS_WARP_FAILED;
+    if (!status && launch_wavefront(s, resolve_kind(RNNT_LSE_AUTO, false), p, pairs, alphas, betas, ll, bad, costs, 0,
+                                    1, U) != cudaSuccess)
+        status = RNNT_STATUS_WARP_FAILED;
+    if (!status) {
+        ExpandSrc src = {};
+        src.pairs = pairs; src.alphas = alphas; src.betas = betas; src.bad = bad;
+        src.labels = labels; src.fastemit_lambda = fastemit_lambda;
+        if (launch_expand(s, p, src, grads, cells, V, blank) != cudaSuccess) status = RNNT_STATUS_GRADS_BLANK_FAILED;
+    }
+    cudaFreeAsync(tmp, s);
+    return status;
+}
+
+int run_warp_rnnt_gather(void *stream, unsigned int *counts, float *alphas, float *betas, const float *log_probs,
+                         float *grads, float *costs, const int *xn, const int *yn, int N, int T, int U,
+                         float fastemit_lambda) {
+    (void)counts;
+    if (!dense_args_ok(N, T, U, 2)) return RNNT_STATUS_WARP_FAILED;
+    if (N == 0) return RNNT_STATUS_SUCCESS;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t cells = (int64_t)N * T * U;
+    const size_t llb = align_up(sizeof(float) * 2 * N, 256);
+    char *tmp = nullptr;
+    if (cudaMallocAsync((void **)&tmp, llb + align_up(sizeof(int) * N, 256), s) != cudaSuccess)
+        return RNNT_STATUS_WARP_FAILED;
+    float *ll = (float *)tmp;
+    int *bad = (int *)(tmp + llb);
+    Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
+    const float2 *pr = reinterpret_cast<const float2 *>(log_probs);
+    int status = RNNT_STATUS_SUCCESS;
+    if (launch_wavefront(s, resolve_kind(RNNT_LSE_AUTO, false), p, pr, alphas, betas, ll, bad, costs, 0, 1, U) !=
+        cudaSuccess)
+        status = RNNT_STATUS_WARP_FAILED;
+    if (!status && launch_grads_pairs(s, p, pr, alphas, betas, bad, fastemit_lambda, reinterpret_cast<float2 *>(grads),
+                                      cells) != cudaSuccess)
+        status = RNNT_STATUS_GRADS_BLANK_FAILED;
+    cudaFreeAsync(tmp, s);
+    return status;
+}
+
+// compact variants run on the legacy default stream like the reference (core.h:41-60 has no stream)
+void run_gather_for_compact(const float *xs, const int *ys, const unsigned int *xn, const unsigned int *yn,
+                            float *gather_xs, long *loc, const unsigned int *memPref, const unsigned int *labelPref,
+                            unsigned int N, unsigned int T, unsigned int U, unsigned int V, unsigned int blank) {
+    (void)memPref; (void)labelPref;   // recomputed on device in 64-bit
+    if (N == 0) return;
+    cudaStream_t s = 0;
+    const size_t pb = align_up(sizeof(int64_t) * N, 256);
+    char *tmp = nullptr;
+    if (cudaMallocAsync((void **)&tmp, 2 * pb + 256, s) != cudaSuccess) compat_die("rnnt loss gather for compact", RNNT_STATUS_GATHER_FAILED);
+    int64_t *mp = (int64_t *)tmp, *lp = (int64_t *)(tmp + pb);
+    int *totals = (int *)(tmp + 2 * pb);
+    const int *xi = (const int *)xn, *yi = (const int *)yn;
+    bool ok = launch_prefix(s, xi, yi, (int)N, mp, lp, totals) == cudaSuccess;
+    Problem p = {xi, yi, mp, lp, (int)N, 0, 0, 1};
+    ok = ok && launch_gather(s, p, xs, ys, (int)V, (int)blank, reinterpret_cast<float2 *>(gather_xs),
+                             reinterpret_cast<int64_t *>(loc), (int64_t)N * T * U) == cudaSuccess;
+    cudaFreeAsync(tmp, s);
+    if (!ok) compat_die("rnnt loss gather for compact", RNNT_STATUS_GATHER_FAILED);
+}
+
+void run_warp_rnnt_compact(unsigned int *counts, float *alphas, float *betas, const float *log_probs, float *grads,
+                           float *costs, const unsigned int *xn, const unsigned int *yn, const unsigned int *memPref,
+                           const unsigned int *labelPref, unsigned int N, unsigned int T, unsigned int U,
+                           float fastemit_lambda, bool required_grad) {
+    (void)counts; (void)memPref; (void)labelPref; (void)T;
+    if (N == 0) return;
+    cudaStream_t s = 0;
+    const size_t pb = align_up(sizeof(int64_t) * N, 256);
+    const size_t llb = align_up(sizeof(float) * 2 * N, 256);
+    char *tmp = nullptr;
+    if (cudaMallocAsync((void **)&tmp, 2 * pb + llb + 256, s) != cudaSuccess) compat_die("rnnt loss compact betas", RNNT_STATUS_WARP_FAILED);
+    int64_t *mp = (int64_t *)tmp, *lp = (int64_t *)(tmp + pb);
+    float *ll = (float *)(tmp + 2 * pb);
+    int *totals = (int *)(tmp + 2 * pb + llb);
+    const int *xi = (const int *)xn, *yi = (const int *)yn;
+    bool ok = launch_prefix(s, xi, yi, (int)N, mp, lp, totals) == cudaSuccess;
+    Problem p = {xi, yi, mp, lp, (int)N, 0, 0, 1};
+    const float2 *pr = reinterpret_cast<const float2 *>(log_probs);
+    ok = ok && launch_wavefront(s, resolve_kind(RNNT_LSE_AUTO, true), p, pr, alphas, betas, ll, nullptr, costs,
+                                required_grad ? 0 : 1, 0, (int)U) == cudaSuccess;
+    if (ok && required_grad)
+        ok = launch_grads_pairs(s, p, pr, alphas, betas, nullptr, fastemit_lambda, reinterpret_cast<float2 *>(grads),
+                                (int64_t)N * T * U) == cudaSuccess;
+    cudaFreeAsync(tmp, s);
+    if (!ok) compat_die("rnnt loss compact", RNNT_STATUS_WARP_FAILED);
+}
+
+void run_scatter_grad_for_compact(const float *grad_cost, const float *gather_grad, const long *loc,
+                                  const int *cum_lens, float *scatter_grad, unsigned int STU, unsigned int N,
+                                  unsigned int V, unsigned int blank) {
+    const int st = rnnt_b200_compact_backward(nullptr, grad_cost, gather_grad, reinterpret_cast<const int64_t *>(loc),
+                                              cum_lens, scatter_grad, (int64_t)STU, (int)N, (int)V, (int)blank);
+    if (st != RNNT_STATUS_SUCCESS) compat_die("rnnt loss filling scatter grad", st);
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+// expand.cu -- dense gradient emit: every element of the (cells, V) output is written exactly once
+// (zeros + the <= 2 non-zeros of each row), with 128-bit streaming stores.
+//
+// What it replaces in the reference (/root/reference):
+//   at::zeros_like(xs) dense memset                 pytorch_binding/binding.cpp:58
+//   kernel_grads_blank / kernel_grads_label         core.cu:260-332  (4-byte stores at stride U*V)
+//   RNNTLoss.backward grads.mul_(grad_output)       pytorch_binding/warp_rnnt/__init__.py:21-24
+//   torch GatherBackward (zeros + scatter_add_)     __init__.py:118-128 (python-level gather=True)
+//   torch::zeros({STU,V}) + kernel_fill_scatter_grad   binding.cpp:239, core_compact.cu:456-484
+//
+// The output is treated as one flat float stream cut into chunks of R consecutive rows; a CTA
+// first stages the R rows' (blank grad, label grad, label id) in shared memory (coalesced reads
+// of alpha/beta/pairs or of the (cells,2) pair grads), then all its threads sweep the chunk with
+// float4 stores, composing each vector from the staged values.  HBM traffic = 4*V bytes written
+// + <= 24 bytes read per row; no pre-zeroing pass, no second pass.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace rnnt {
+
+constexpr int kExpandThreads = 256;
+constexpr int kExpandMaxRows = 256;
+
+// same arithmetic as k_grads_pairs (core.cu:284-294, :319-331)
+__device__ __forceinline__ float2 cell_grads_ab(const Lattice &L, const ExpandSrc &src, int t, int u, float b00) {
+    const int64_t c = L.base + (int64_t)t * L.stride + u;
+    const float2 w = src.pairs[c];
+    const float al = src.alphas[c];
+    float gb = 0.0f, gl = 0.0f;
+    const bool last_t = (t == L.Tn - 1), last_u = (u == L.Un - 1);
+    if (!(last_t && !last_u)) {
+        float a = al;
+        if (!last_t) a += src.betas[c + L.stride];
+        a = expf(a + w.x - b00);
+        gb = -a;
+    }
+    if (!last_u) {
+        float a = al + src.betas[c + 1];
+        a = expf(a + w.y - b00);
+        a = (float)((1.0 + (double)src.fastemit_lambda) * (double)a);
+        gl = -a;
+    }
+    return make_float2(gb, gl);
+}
+
+// MODE 0: dense layout, source = alpha/beta/pairs (forward)            label overrides blank
+// MODE 1: dense layout, source = pair grads (gather=True backward)     label adds to blank (scatter_add)
+// MODE 2: compact layout, source = pair grads + loc (compact backward) label written iff loc != blank
+template <int MODE>
+__global__ void __launch_bounds__(kExpandThreads)
+k_expand(Problem p, ExpandSrc src, float *__restrict__ out, int64_t cells, int V, int blank, int rows_per_chunk,
+         FastDiv divV, FastDiv divU, FastDiv divTU, int vec_ok) {
+    __shared__ float2 s_g[kExpandMaxRows];
+    __shared__ int s_lab[kExpandMaxRows];
+    const int64_t nchunks = (cells + rows_per_chunk - 1) / rows_per_chunk;
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const int64_t r0 = chunk * rows_per_chunk;
+        const int rows = (int)min((int64_t)rows_per_chunk, cells - r0);
+        __syncthreads();  // previous chunk's sweep is done with s_g / s_lab
+        // ---- phase 1: stage the rows' non-zeros
+        for (int r = threadIdx.x; r < rows; r += kExpandThreads) {
+            const int64_t c = r0 + r;
+            float2 g = make_float2(0.0f, 0.0f);
+            int lab = -1;
+            if (MODE == 2) {
+                // which sample? binary search in the inclusive cumsum (core_compact.cu:465-477)
+                int lo = 0, hi = p.N - 1;
+                while (lo <= hi) {
+                    const int mid = lo + (hi - lo) / 2;
+                    if (c >= (int64_t)src.cum_lens[mid]) lo = mid + 1; else hi = mid - 1;
+                }
+                const int n = min(lo, p.N - 1);
+                const float sc = src.scale ? src.scale[n] : 1.0f;
+                const float2 q = src.pg[c];
+                g = make_float2(q.x * sc, q.y * sc);
+                const int64_t l = src.loc[c];
+                lab = (l != (int64_t)blank) ? (int)l : -1;
+            } else {
+                uint32_t n, rem, t, u;
+                divTU.divmod((uint32_t)c, n, rem);
+                divU.divmod(rem, t, u);
+                if (MODE == 1) {
+                    const float sc = src.scale ? src.scale[n] : 1.0f;
+                    const float2 q = src.pg[c];
+                    g = make_float2(q.x * sc, q.y * sc);
+                    if ((int)u < p.U - 1) lab = src.labels[(int64_t)n * (p.U - 1) + u];
+                } else {
+                    const Lattice L = get_lattice(p, (int)n);
+                    const bool live = L.ok && !(src.bad && src.bad[n]);
+                    if (live && (int)t < L.Tn && (int)u < L.Un) {
+                        g = cell_grads_ab(L, src, (int)t, (int)u, src.betas[L.base]);
+                        if (src.scale) { const float sc = src.scale[n]; g.x *= sc; g.y *= sc; }
+                        if ((int)u < L.Un - 1) lab = src.labels[L.lab_base + u];
+                    }
+                }
+            }
+            s_g[r] = g;
+            s_lab[r] = lab;
+        }
+        __syncthreads();
+        // ---- phase 2: sweep the chunk's floats [f0, f1)
+        const int64_t f0 = r0 * (int64_t)V;
+        const int64_t f1 = f0 + (int64_t)rows * V;
+        auto value = [&](int row, int v) -> float {
+            const float2 g = s_g[row];
+            const int lab = s_lab[row];
+            float x = (v == blank) ? g.x : 0.0f;
+            if (v == lab) x = (MODE == 1 && src.label_adds) ? x + g.y : g.y;
+            return x;
+        };
+        int64_t a0 = vec_ok ? min(f1, (f0 + 3) & ~(int64_t)3) : f1;
+        int64_t a1 = vec_ok ? max(a0, f1 & ~(int64_t)3) : f1;
+        // head and tail scalars (at most 3 each when vec_ok)
+        for (int64_t f = f0 + threadIdx.x; f < a0; f += kExpandThreads) {
+            const uint32_t local = (uint32_t)(f - f0);
+            const uint32_t row = divV.div(local);
+            st_cs(out + f, value((int)row, (int)(local - row * V)));
+        }
+        for (int64_t f = a1 + threadIdx.x; f < f1; f += kExpandThreads) {
+            const uint32_t local = (uint32_t)(f - f0);
+            const uint32_t row = divV.div(local);
+            st_cs(out + f, value((int)row, (int)(local - row * V)));
+        }
+        for (int64_t f = a0 + 4 * (int64_t)threadIdx.x; f < a1; f += 4 * kExpandThreads) {
+            const uint32_t local = (uint32_t)(f - f0);
+            uint32_t row = divV.div(local);
+            int v = (int)(local - row * V);
+            float e[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                e[k] = value((int)row, v);
+                if (++v == V) { v = 0; ++row; }
+            }
+            st_cs_v4(out + f, make_float4(e[0], e[1], e[2], e[3]));
+        }
+    }
+}
+
+cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src, float *out, int64_t cells,
+                          int V, int blank) {
+    if (cells <= 0) return cudaSuccess;
+    int rows = (int)(65536 / ((int64_t)V * 4));
+    rows = max(1, min(rows, kExpandMaxRows));
+    const int64_t nchunks = (cells + rows - 1) / rows;
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)(nchunks < (int64_t)sms * 8 ? nchunks : (int64_t)sms * 8);
+    const FastDiv divV((uint32_t)V), divU((uint32_t)max(p.U, 1)), divTU((uint32_t)max(p.T * p.U, 1));
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) ? 1 : 0;
+    const int mode = p.compact ? 2 : (src.pg ? 1 : 0);
+    if (mode == 0) k_expand<0><<<grid, kExpandThreads, 0, s>>>(p, src, out, cells, V, blank, rows, divV, divU, divTU, vec_ok);
+    else if (mode == 1) k_expand<1><<<grid, kExpandThreads, 0, s>>>(p, src, out, cells, V, blank, rows, divV, divU, divTU, vec_ok);
+    else k_expand<2><<<grid, kExpandThreads, 0, s>>>(p, src, out, cells, V, blank, rows, divV, divU, divTU, vec_ok);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace rnnt

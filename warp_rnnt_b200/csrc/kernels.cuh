@@ -1,0 +1,39 @@
+// kernels.cuh -- host-side launch entry points shared between the .cu files and api.cu.
+#pragma once
+#include "common.cuh"
+
+namespace rnnt {
+
+void count_launch();   // api.cu: bumps the library-wide launch counter
+
+cudaError_t launch_prefix(cudaStream_t s, const int *xn, const int *yn, int N, int64_t *mem_pref,
+                          int64_t *lab_pref, int *totals);
+cudaError_t launch_gather(cudaStream_t s, const Problem &p, const float *lp, const int *labels, int V, int blank,
+                          float2 *pairs, int64_t *loc, int64_t cells_hint);
+cudaError_t launch_wavefront(cudaStream_t s, int kind, const Problem &p, const float2 *pairs, float *alphas,
+                             float *betas, float *ws_ll, int *bad, float *costs, int beta_only, int guard,
+                             int u_hint);
+cudaError_t launch_grads_pairs(cudaStream_t s, const Problem &p, const float2 *pairs, const float *alphas,
+                               const float *betas, const int *bad, float fastemit_lambda, float2 *out,
+                               int64_t cells_hint);
+
+// expand.cu -- dense gradient emit (every element of `out` is written)
+struct ExpandSrc {
+    // source A: alpha/beta/pairs (forward, dense layout)      -> pg == nullptr
+    // source B: pair grads (cells,2) (+ per-sample scale)     -> pg != nullptr
+    const float2 *pairs;
+    const float *alphas;
+    const float *betas;
+    const int *bad;
+    const float2 *pg;
+    const float *scale;      // (N) or nullptr
+    const int *labels;       // dense: (N,U-1)
+    const int64_t *loc;      // compact backward: label id per cell (blank on the last column)
+    const int *cum_lens;     // compact backward: inclusive cumsum of xn*(yn+1), (N)
+    float fastemit_lambda;
+    int label_adds;          // 1: label == blank accumulates (torch scatter_add semantics of gather=True)
+};
+cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src, float *out, int64_t cells,
+                          int V, int blank);
+
+}  // namespace rnnt
