@@ -112,12 +112,13 @@ int rnnt_b200_gather_backward(void *stream, const float *pair_grads, const int *
  * prefix sums / .item() syncs of binding.cpp:132-158 (prefix sums are computed on device).
  *   pair_grads (STU,2) out or NULL (forward only = the reference's required_grad=false)
  *   loc (STU) i64 out or NULL: label id per cell, blank on each sample's last column
- *   totals (4) i32 out or NULL: {sum xn*(yn+1), sum yn, max xn, max yn+1} for host validation */
+ *   totals (4) i32 out or NULL: {sum xn*(yn+1), sum yn, max xn, max yn+1} for host validation
+ *   max_T, max_U: launch-shaping hints (upper bounds of xn and yn+1), 0 = unknown */
 int rnnt_b200_compact_forward(void *stream, void *workspace, size_t workspace_bytes,
                               const float *xs, const int *ys, const int *xn, const int *yn,
                               float *costs, float *pair_grads, int64_t *loc, int *totals,
                               int64_t STU, int N, int V, int blank, float fastemit_lambda,
-                              int lse_mode);
+                              int lse_mode, int max_T, int max_U);
 
 /* totals (4) i32 out = {sum xn*(yn+1), sum yn, max xn, max yn+1} (each clamped to INT32_MAX):
  * lets a binding validate shapes with ONE small device->host copy instead of the reference's

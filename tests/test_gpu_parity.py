@@ -19,6 +19,12 @@ pytestmark = pytest.mark.gpu
 MODES = ["fast", "exact"]
 
 
+def gtol(T, U):
+    """fp32 alpha/beta carry ~ulp(|alpha|) rounding per anti-diagonal; the compiled reference shows the
+    same distance to the fp64 oracle (see test_reference_noise_floor).  Grows with the path length."""
+    return 2e-5 + 6e-6 * (T + U)
+
+
 @pytest.fixture(scope="module")
 def w():
     import warp_rnnt_b200
@@ -109,7 +115,7 @@ def test_calls_smoke(w, capfd):
         torch.cuda.synchronize()
         c0, g0 = oracle.dense(xs.numpy(), ys.numpy(), xn.numpy(), yn.numpy())
         np.testing.assert_allclose(costs.cpu().numpy(), c0, rtol=1e-5)
-        np.testing.assert_allclose(grads.cpu().numpy(), g0, atol=2e-5)
+        np.testing.assert_allclose(grads.cpu().numpy(), g0, atol=1e-4)   # T+U = 190 fp32 steps
     assert "WARNING" not in capfd.readouterr().out
 
 
@@ -139,7 +145,7 @@ def test_dense_vs_oracle(w, shape, mode):
     costs, grads = w._C.rnnt_loss(cu(lp), cu(ys), cu(xn), cu(yn), blank=blank, fastemit_lambda=lam)
     c0, g0 = oracle.dense(lp, ys, xn, yn, blank=blank, fastemit_lambda=lam)
     np.testing.assert_allclose(costs.cpu().numpy(), c0, rtol=2e-6)
-    np.testing.assert_allclose(grads.cpu().numpy(), g0, atol=2e-5)
+    np.testing.assert_allclose(grads.cpu().numpy(), g0, atol=gtol(T, U))
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -152,7 +158,7 @@ def test_gathered_input_vs_oracle(w, shape, mode):
     costs, grads = w._C.rnnt_loss(cu(g), cu(ys), cu(xn), cu(yn), blank=-1, fastemit_lambda=lam)
     c0, g0 = oracle.dense(g, ys, xn, yn, blank=-1, fastemit_lambda=lam)
     np.testing.assert_allclose(costs.cpu().numpy(), c0, rtol=2e-6)
-    np.testing.assert_allclose(grads.cpu().numpy(), g0, atol=2e-5)
+    np.testing.assert_allclose(grads.cpu().numpy(), g0, atol=gtol(T, U))
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -165,13 +171,13 @@ def test_compact_vs_oracle(w, shape, mode):
     costs, pg, loc = w._C.rnnt_loss_compact(cu(xs_c), cu(ys_c), cu(xn), cu(yn), blank=blank, fastemit_lambda=lam)
     c0, pg0, loc0 = oracle.compact(xs_c, ys_c, xn, yn, blank=blank, fastemit_lambda=lam)
     np.testing.assert_allclose(costs.cpu().numpy(), c0, rtol=2e-6)
-    np.testing.assert_allclose(pg.cpu().numpy(), pg0, atol=2e-5)
+    np.testing.assert_allclose(pg.cpu().numpy(), pg0, atol=gtol(T, U))
     assert np.array_equal(loc.cpu().numpy(), loc0)
     cum = np.cumsum(xn.astype(np.int64) * (yn + 1)).astype(np.int32)
     go = np.linspace(0.5, 2.0, N).astype(np.float32)
     out = w._C.rnnt_loss_compact_backward(cu(go), pg, cu(cum), loc, V, blank)
     out0 = oracle.compact_scatter(go, pg0, loc0, cum, V, blank)
-    np.testing.assert_allclose(out.cpu().numpy(), out0, atol=4e-5)
+    np.testing.assert_allclose(out.cpu().numpy(), out0, atol=2 * gtol(T, U))
     # forward only (required_grad=False, __init__.py:109-116)
     costs2, _, _ = w._C.rnnt_loss_compact(cu(xs_c), cu(ys_c), cu(xn), cu(yn), blank=blank,
                                           fastemit_lambda=lam, required_grad=False)
@@ -207,7 +213,7 @@ def test_python_api_autograd(w, gather, reduction, avg):
         loss.backward()
         loss0, g0 = oracle.rnnt_loss(lp, ys, xn, yn, avg, reduction, 0, gather, 0.1)
     np.testing.assert_allclose(loss.detach().cpu().numpy(), loss0, rtol=1e-5)
-    np.testing.assert_allclose(x.grad.cpu().numpy(), g0, atol=2e-5)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g0, atol=2 * gtol(T, U))
 
 
 def test_python_api_compact_autograd(w):
@@ -288,7 +294,7 @@ def test_exact_mode_is_bit_identical_to_reference_dense(w, ref, shape):
     w.set_lse_mode("fast")
     cf, gf = w._C.rnnt_loss(*args, blank=blank, fastemit_lambda=lam)
     assert ((cf - cr).abs() / cr.abs()).max().item() <= 1e-5
-    assert (gf - gr).abs().max().item() <= 2e-5
+    assert (gf - gr).abs().max().item() <= gtol(T, U)
 
 
 @pytest.mark.parametrize("shape", REF_SHAPES)
@@ -307,7 +313,15 @@ def test_exact_mode_is_bit_identical_to_reference_gather_and_compact(w, ref, sha
     cargs = (cu(xs_c), cu(ys_c), cu(xn), cu(yn))
     cr, gr, lr = ref.rnnt_loss_compact(*cargs, blank=blank, fastemit_lambda=lam)
     cm, gm, lm = w._C.rnnt_loss_compact(*cargs, blank=blank, fastemit_lambda=lam)
-    assert torch.equal(cm, cr) and torch.equal(gm, gr) and torch.equal(lm, lr)
+    assert torch.equal(cm, cr) and torch.equal(lm, lr)
+    assert torch.equal(gm[:, 0], gr[:, 0])
+    # The reference never writes the label slot of a sample's last column when that sample has the
+    # batch's maximum label length (grid.y = U-1 in core_compact.cu:392 never reaches u == yn[n]),
+    # so those entries of its torch::empty buffer are uninitialised; they are ignored by the
+    # backward (loc == blank, core_compact.cu:482).  Compare the defined entries only.
+    used = lr != blank
+    assert torch.equal(gm[:, 1][used], gr[:, 1][used])
+    assert torch.all(gm[:, 1][~used] == 0)
     cumlen = torch.cumsum(cu(xn) * (cu(yn) + 1), dim=0, dtype=torch.int32)
     go = torch.linspace(0.5, 1.5, N).cuda()
     br = ref.rnnt_loss_compact_backward(go, gr, cumlen, lr, V, blank)

@@ -45,6 +45,17 @@ static int resolve_kind(int lse_mode, bool compact) {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// RNNT_B200_PATH = auto | fused | general  (tests exercise both paths on the same inputs)
+static int g_path = -1;
+static bool want_fused(int N, int T, int U, FusedPlan *plan) {
+    if (g_path < 0) {
+        const char *e = getenv("RNNT_B200_PATH");
+        g_path = (e && !strcmp(e, "general")) ? 2 : (e && !strcmp(e, "fused")) ? 1 : 0;
+    }
+    if (g_path == 2) return false;
+    return fused_plan(N, T, U, plan);
+}
+
 struct Workspace {
     float2 *pairs;
     float *alphas, *betas, *ll;
@@ -132,12 +143,19 @@ int rnnt_b200_loss_dense(void *stream, void *workspace, size_t workspace_bytes, 
     if (N == 0) return RNNT_STATUS_SUCCESS;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t cells = (int64_t)N * T * U;
+    FusedPlan plan;
+    if (want_fused(N, T, U, &plan)) {
+        RNNT_TRY(launch_fused(s, resolve_kind(lse_mode, false), plan, log_probs, labels, xn, yn, costs, grads, nullptr,
+                              grad_scale, N, T, U, V, blank, fastemit_lambda, 0, 1),
+                 RNNT_STATUS_WARP_FAILED);
+        return RNNT_STATUS_SUCCESS;
+    }
     const Workspace w = carve(workspace, cells, N);
     if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
     Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
     RNNT_TRY(launch_gather(s, p, log_probs, labels, V, blank, w.pairs, nullptr, cells), RNNT_STATUS_GATHER_FAILED);
     RNNT_TRY(launch_wavefront(s, resolve_kind(lse_mode, false), p, w.pairs, w.alphas, w.betas, w.ll, w.bad, costs,
-                              grads == nullptr, 1, U),
+                              grads == nullptr, 1, T, U),
              RNNT_STATUS_WARP_FAILED);
     if (grads) {
         ExpandSrc src = {};
@@ -157,12 +175,19 @@ int rnnt_b200_loss_pairs(void *stream, void *workspace, size_t workspace_bytes, 
     if (N == 0) return RNNT_STATUS_SUCCESS;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t cells = (int64_t)N * T * U;
+    FusedPlan plan;
+    if (want_fused(N, T, U, &plan)) {
+        RNNT_TRY(launch_fused(s, resolve_kind(lse_mode, false), plan, pairs, nullptr, xn, yn, costs, nullptr,
+                              reinterpret_cast<float2 *>(pair_grads), nullptr, N, T, U, 2, 0, fastemit_lambda, 1, 1),
+                 RNNT_STATUS_WARP_FAILED);
+        return RNNT_STATUS_SUCCESS;
+    }
     const Workspace w = carve(workspace, cells, N);
     if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
     Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
     const float2 *pr = reinterpret_cast<const float2 *>(pairs);
     RNNT_TRY(launch_wavefront(s, resolve_kind(lse_mode, false), p, pr, w.alphas, w.betas, w.ll, w.bad, costs,
-                              pair_grads == nullptr, 1, U),
+                              pair_grads == nullptr, 1, T, U),
              RNNT_STATUS_WARP_FAILED);
     if (pair_grads)
         RNNT_TRY(launch_grads_pairs(s, p, pr, w.alphas, w.betas, w.bad, fastemit_lambda,
@@ -179,12 +204,19 @@ int rnnt_b200_gather_forward(void *stream, void *workspace, size_t workspace_byt
     if (N == 0) return RNNT_STATUS_SUCCESS;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t cells = (int64_t)N * T * U;
+    FusedPlan plan;
+    if (want_fused(N, T, U, &plan)) {
+        RNNT_TRY(launch_fused(s, resolve_kind(lse_mode, false), plan, log_probs, labels, xn, yn, costs, nullptr,
+                              reinterpret_cast<float2 *>(pair_grads), nullptr, N, T, U, V, blank, fastemit_lambda, 0, 1),
+                 RNNT_STATUS_WARP_FAILED);
+        return RNNT_STATUS_SUCCESS;
+    }
     const Workspace w = carve(workspace, cells, N);
     if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
     Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
     RNNT_TRY(launch_gather(s, p, log_probs, labels, V, blank, w.pairs, nullptr, cells), RNNT_STATUS_GATHER_FAILED);
     RNNT_TRY(launch_wavefront(s, resolve_kind(lse_mode, false), p, w.pairs, w.alphas, w.betas, w.ll, w.bad, costs,
-                              pair_grads == nullptr, 1, U),
+                              pair_grads == nullptr, 1, T, U),
              RNNT_STATUS_WARP_FAILED);
     if (pair_grads)
         RNNT_TRY(launch_grads_pairs(s, p, w.pairs, w.alphas, w.betas, w.bad, fastemit_lambda,
@@ -212,7 +244,7 @@ int rnnt_b200_gather_backward(void *stream, const float *pair_grads, const int *
 int rnnt_b200_compact_forward(void *stream, void *workspace, size_t workspace_bytes, const float *xs, const int *ys,
                               const int *xn, const int *yn, float *costs, float *pair_grads, int64_t *loc,
                               int *totals, int64_t STU, int N, int V, int blank, float fastemit_lambda,
-                              int lse_mode) {
+                              int lse_mode, int max_T, int max_U) {
     if (N < 0 || STU < 0 || V < 1 || V >= (1 << 22) || blank < 0 || blank >= V) return RNNT_STATUS_INVALID_ARGUMENT;
     if (reinterpret_cast<uintptr_t>(pair_grads) & 7u) return RNNT_STATUS_INVALID_ARGUMENT;
     if (N == 0) return RNNT_STATUS_SUCCESS;
@@ -224,7 +256,7 @@ int rnnt_b200_compact_forward(void *stream, void *workspace, size_t workspace_by
     RNNT_TRY(launch_gather(s, p, xs, ys, V, blank, w.pairs, loc, STU), RNNT_STATUS_GATHER_FAILED);
     // no mismatch guard in the compact reference (core_compact.cu:347-358)
     RNNT_TRY(launch_wavefront(s, resolve_kind(lse_mode, true), p, w.pairs, w.alphas, w.betas, w.ll, w.bad, costs,
-                              pair_grads == nullptr, 0, 512),
+                              pair_grads == nullptr, 0, max_T, max_U),
              RNNT_STATUS_WARP_FAILED);
     if (pair_grads)
         RNNT_TRY(launch_grads_pairs(s, p, w.pairs, w.alphas, w.betas, nullptr, fastemit_lambda,
@@ -284,7 +316,7 @@ int run_warp_rnnt(void *stream, unsigned int *counts, float *alphas, float *beta
     if (launch_gather(s, p, log_probs, labels, V, blank, pairs, nullptr, cells) != cudaSuccess)
         status = RNNT_STATUS_WARP_FAILED;
     if (!status && launch_wavefront(s, resolve_kind(RNNT_LSE_AUTO, false), p, pairs, alphas, betas, ll, bad, costs, 0,
-                                    1, U) != cudaSuccess)
+                                    1, T, U) != cudaSuccess)
         status = RNNT_STATUS_WARP_FAILED;
     if (!status) {
         ExpandSrc src = {};
@@ -313,7 +345,7 @@ int run_warp_rnnt_gather(void *stream, unsigned int *counts, float *alphas, floa
     Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
     const float2 *pr = reinterpret_cast<const float2 *>(log_probs);
     int status = RNNT_STATUS_SUCCESS;
-    if (launch_wavefront(s, resolve_kind(RNNT_LSE_AUTO, false), p, pr, alphas, betas, ll, bad, costs, 0, 1, U) !=
+    if (launch_wavefront(s, resolve_kind(RNNT_LSE_AUTO, false), p, pr, alphas, betas, ll, bad, costs, 0, 1, T, U) !=
         cudaSuccess)
         status = RNNT_STATUS_WARP_FAILED;
     if (!status && launch_grads_pairs(s, p, pr, alphas, betas, bad, fastemit_lambda, reinterpret_cast<float2 *>(grads),
@@ -348,7 +380,7 @@ void run_warp_rnnt_compact(unsigned int *counts, float *alphas, float *betas, co
                            float *costs, const unsigned int *xn, const unsigned int *yn, const unsigned int *memPref,
                            const unsigned int *labelPref, unsigned int N, unsigned int T, unsigned int U,
                            float fastemit_lambda, bool required_grad) {
-    (void)counts; (void)memPref; (void)labelPref; (void)T;
+    (void)counts; (void)memPref; (void)labelPref;
     if (N == 0) return;
     cudaStream_t s = 0;
     const size_t pb = align_up(sizeof(int64_t) * N, 256);
@@ -363,7 +395,7 @@ void run_warp_rnnt_compact(unsigned int *counts, float *alphas, float *betas, co
     Problem p = {xi, yi, mp, lp, (int)N, 0, 0, 1};
     const float2 *pr = reinterpret_cast<const float2 *>(log_probs);
     ok = ok && launch_wavefront(s, resolve_kind(RNNT_LSE_AUTO, true), p, pr, alphas, betas, ll, nullptr, costs,
-                                required_grad ? 0 : 1, 0, (int)U) == cudaSuccess;
+                                required_grad ? 0 : 1, 0, (int)T, (int)U) == cudaSuccess;
     if (ok && required_grad)
         ok = launch_grads_pairs(s, p, pr, alphas, betas, nullptr, fastemit_lambda, reinterpret_cast<float2 *>(grads),
                                 (int64_t)N * T * U) == cudaSuccess;

@@ -124,6 +124,7 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> rnnt_loss_compact(const at::Tenso
     // placeholder the caller must not use
     at::Tensor grads = required_grad ? at::empty({STU, 2}, xs.options()) : at::empty({0}, xs.options());
     if (N == 0) return std::make_tuple(costs, grads, loc);
+    int max_T = 0, max_U = 0;
     // shape validation: one 16-byte device->host copy (the reference needs four .item() syncs)
     {
         at::Tensor scratch = at::empty({2 * N}, xs.options().dtype(at::kLong));
@@ -134,13 +135,15 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> rnnt_loss_compact(const at::Tenso
         const int *t = h.data_ptr<int>();
         TORCH_CHECK(ys.numel() == t[1], "ys shape must be equal to (sum(yn), )");
         TORCH_CHECK(STU == t[0], "xs shape mismatch with (\\sum{xn*(yn+1)}, )");
+        max_T = t[2];
+        max_U = t[3];
     }
     at::Tensor ws = workspace_for(xs, STU, N);
     check_status(rnnt_b200_compact_forward(stream, ws.data_ptr(), (size_t)ws.numel(), xs.data_ptr<float>(),
                                            ys.data_ptr<int>(), xn.data_ptr<int>(), yn.data_ptr<int>(),
                                            costs.data_ptr<float>(), required_grad ? grads.data_ptr<float>() : nullptr,
                                            loc.data_ptr<int64_t>(), nullptr, STU, (int)N, (int)V, blank,
-                                           fastemit_lambda, RNNT_LSE_AUTO));
+                                           fastemit_lambda, RNNT_LSE_AUTO, max_T, max_U));
     return std::make_tuple(costs, grads, loc);
 }
 

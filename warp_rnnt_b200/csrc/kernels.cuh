@@ -12,7 +12,7 @@ cudaError_t launch_gather(cudaStream_t s, const Problem &p, const float *lp, con
                           float2 *pairs, int64_t *loc, int64_t cells_hint);
 cudaError_t launch_wavefront(cudaStream_t s, int kind, const Problem &p, const float2 *pairs, float *alphas,
                              float *betas, float *ws_ll, int *bad, float *costs, int beta_only, int guard,
-                             int u_hint);
+                             int t_hint, int u_hint);
 cudaError_t launch_grads_pairs(cudaStream_t s, const Problem &p, const float2 *pairs, const float *alphas,
                                const float *betas, const int *bad, float fastemit_lambda, float2 *out,
                                int64_t cells_hint);
@@ -35,5 +35,13 @@ struct ExpandSrc {
 };
 cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src, float *out, int64_t cells,
                           int V, int blank);
+
+// fused.cu -- single-kernel path for lattices that fit shared memory
+struct FusedPlan { int W, ring, nw, slices; size_t smem; };
+bool fused_plan(int N, int T, int U, FusedPlan *plan);
+cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const float *lp, const int *labels,
+                         const int *xn, const int *yn, float *costs, float *grads, float2 *pair_grads,
+                         const float *scale, int N, int T, int U, int V, int blank, float lam, int pairs_in,
+                         int guard);
 
 }  // namespace rnnt

@@ -146,8 +146,7 @@ k_gather(Problem p, const float *__restrict__ lp, const int *__restrict__ labels
 // ------------------------------------------------------------------------------------------
 // k_wavefront
 // ------------------------------------------------------------------------------------------
-constexpr int kRing = 128;     // boundary ring slots per warp boundary
-constexpr int kPrefetch = 8;   // steps of log-prob prefetch (registers)
+constexpr int kPrefetch = 8;   // steps of log-prob prefetch per register buffer (double-buffered)
 
 struct __align__(8) Slot { float val; int row; };
 
@@ -173,39 +172,190 @@ __device__ __forceinline__ void st_vol_s32(int *p, int v) {
     asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 
+// Predicated global loads whose destination register is written by the load itself.
+__device__ __forceinline__ float ldg_nc_pred(const float *p, bool pred, float dflt) {
+    float v;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\tmov.f32 %0, %3;\n\t@p ld.global.nc.f32 %0, [%1];\n\t}"
+                 : "=f"(v)
+                 : "l"(p), "r"((int)pred), "f"(dflt));
+    return v;
+}
+__device__ __forceinline__ float ldg_cg_pred(const float *p, bool pred, float dflt) {
+    float v;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\tmov.f32 %0, %3;\n\t@p ld.global.cg.f32 %0, [%1];\n\t}"
+                 : "=f"(v)
+                 : "l"(p), "r"((int)pred), "f"(dflt)
+                 : "memory");
+    return v;
+}
+
+// Where lane 0 of a warp gets its left-hand neighbour column from.
+enum LeftSrc { kLeftNone = 0,   // lattice column 0: no left neighbour
+               kLeftRing = 1,   // previous warp of this CTA, through the shared-memory ring
+               kLeftMem = 2 };  // global memory: previous column pass (U > 32*nwarps), or -- with
+                                // `override` -- the pre-computed column 0 of the exact mode
+
+// Per-warp state of one sweep over the warp's 32 columns.
+struct Sweep {
+    const float2 *pr;   // pairs of this lattice
+    float *o;           // alpha or beta of this lattice
+    Slot *ring_in, *ring_out;
+    int *cons_self, *cons_next;
+    int Tn, Un, st, T1, U1;
+    int j, lane;
+    int nsteps, ring_mask;
+    bool col_ok, publish, backpressure, override0;
+};
+
+// "Minus infinity" that stays finite: cells outside the lattice carry kBig so that the one uniform
+// step below needs no per-lane control flow.  LSE(x, kBig) == x and LSE(kBig, kBig) == kBig (+ln 2,
+// absorbed) exactly, in every LSE flavour, and kBig + (any log-prob) stays ~kBig without ever
+// producing inf - inf.
+constexpr float kBig = -1.0e30f;
+
 // One direction of one lattice.  "Primed" coordinates (i,j): alpha uses (t,u); beta uses
 // (Tn-1-t, Un-1-u), so both are the same recurrence
 //   val[i,j] = LSE(val[i-1,j] + wB(i,j), val[i,j-1] + wL(i,j)),  val[0,0] = init
 // alpha: wB = blank[i-1,j], wL = label[i,j-1], init 0          (core.cu:80-134)
 // beta : wB = blank[t,u],   wL = label[t,u] at the own cell, init = blank[T-1,U-1]  (core.cu:171-239)
+// Lane l of the warp owns column j and at step s works on row i = s - l.  Edge rules are encoded
+// in the operands instead of branches:
+//   row 0     : val starts at kBig          -> skip term vanishes, v = emit        (core.cu:80-90)
+//   column 0  : wL = kBig for that lane     -> emit term vanishes, v = skip        (core.cu:92-110)
+//   cell (0,0): val starts at 0 with wB(0,0) = 0 (alpha) / blank[T-1,U-1] (beta)   (core.cu:64-66,171-173)
+//   i < 0     : wL = kBig, wB = 0           -> val stays kBig until the lane's first row
+//   i >= Tn   : results are garbage that no in-lattice cell ever reads; stores are masked.
+template <int KIND, bool BETA, int SRC>
+__device__ __forceinline__ float sweep_warp(const Sweep &S) {
+    const int lane = S.lane, j = S.j, Tn = S.Tn, st = S.st, T1 = S.T1, U1 = S.U1;
+    const unsigned rows = S.col_ok ? (unsigned)Tn : 0u;    // (unsigned)i < rows  <=>  cell (i,j) is in the lattice
+    const bool first_col = (j == 0);
+    float val = first_col ? 0.0f : kBig;
+    float last = val;         // value of this lane's last in-lattice row
+    int cons_seen = 0;        // producer-side cache of the consumer's progress counter
+    Slot pre;                 // consumer: ring slot for the next row, loaded one step ahead
+    pre.val = 0.0f;
+    pre.row = -2;
+
+    // own cell index at step s is c0 + s*ds (64-bit): alpha walks down, beta walks up
+    const int64_t ds = BETA ? -(int64_t)st : (int64_t)st;
+    const int64_t c0 = BETA ? ((int64_t)(T1 + lane) * st + (U1 - j)) : (-(int64_t)lane * st + j);
+    // memory-resident left boundary / column-0 override (lane 0 only)
+    const int64_t bcol = S.override0 ? 0 : (BETA ? 1 : -1);
+    const bool mem_lane = (SRC == kLeftMem) && lane == 0;
+
+    float wb[kPrefetch], wl[kPrefetch], bnd[kPrefetch];
+
+    // operands of step s into prefetch slot k.  Predicated loads that write the destination
+    // register directly (a select after the load would make the prefetch wait for its own data).
+    auto fetch = [&](int k, int s) {
+        const int i = s - lane;
+        const bool in = (unsigned)i < rows;
+        const int64_t c = c0 + (int64_t)s * ds;
+        const float *cell = reinterpret_cast<const float *>(S.pr + c);
+        if (BETA) {
+            wb[k] = ldg_nc_pred(cell, in, 0.0f);
+            wl[k] = ldg_nc_pred(cell + 1, in && !first_col, (i < 0 || first_col) ? kBig : 0.0f);
+        } else {
+            wb[k] = ldg_nc_pred(cell - 2 * (int64_t)st, in && i >= 1, 0.0f);
+            wl[k] = ldg_nc_pred(cell - 1, in && !first_col, (i < 0 || first_col) ? kBig : 0.0f);
+        }
+        if (SRC == kLeftMem) bnd[k] = ldg_cg_pred(S.o + c + bcol, in && mem_lane && (!S.override0 || i >= 1), kBig);
+    };
+
+    // consumer side of the ring: value of the left neighbour column at row `row` (warp-uniform call)
+    auto ring_get = [&](int row) -> float {
+        while (pre.row != row) pre = ld_slot(&S.ring_in[row & S.ring_mask]);
+        const float v = pre.val;
+        if (S.backpressure && lane == 0) st_vol_s32(S.cons_self, row + 1);
+        pre = ld_slot(&S.ring_in[(row + 1) & S.ring_mask]);   // next row, off the dependent chain
+        return v;
+    };
+    // producer side: lane 31 hands row `row` of its column to the next warp (warp-uniform call)
+    auto ring_put = [&](int row, float v) {
+        if (S.backpressure && row - S.ring_mask - 1 >= cons_seen) {
+            int c = ld_vol_s32(S.cons_next);
+            while (row - S.ring_mask - 1 >= c) c = ld_vol_s32(S.cons_next);
+            cons_seen = c;
+        }
+        if (lane == 31) st_slot(&S.ring_out[row & S.ring_mask], v, row);
+    };
+
+#pragma unroll
+    for (int k = 0; k < kPrefetch; ++k) fetch(k, k);
+
+    float *op = S.o + c0;
+    for (int s0 = 0; s0 < S.nsteps; s0 += kPrefetch) {
+#pragma unroll
+        for (int k = 0; k < kPrefetch; ++k) {
+            const int s = s0 + k;                               // steps past nsteps are harmless no-ops
+            float left = __shfl_up_sync(0xffffffffu, val, 1);
+            if (SRC == kLeftRing) {
+                if (s < Tn) {                                   // warp-uniform
+                    const float b = ring_get(s);
+                    if (lane == 0) left = b;
+                }
+            } else if (SRC == kLeftMem) {
+                if (lane == 0) left = bnd[k];
+            }
+            const float skip = val + wb[k];
+            const float emit = left + wl[k];
+            float v = lse<KIND>(skip, emit);
+            if (SRC == kLeftMem) {
+                if (S.override0 && lane == 0 && s >= 1) v = bnd[k];   // column 0 from the scan pre-pass
+            }
+            val = v;
+            if ((unsigned)(s - lane) < rows) {
+                *op = v;
+                last = v;
+            }
+            op += ds;
+            if (S.publish && (unsigned)(s - 31) < (unsigned)Tn) ring_put(s - 31, v);   // warp-uniform
+            fetch(k, s + kPrefetch);                            // rolling prefetch, kPrefetch steps ahead
+        }
+    }
+    return last;
+}
+
 template <int KIND, bool BETA>
 __device__ void wavefront_dir(const Lattice &L, const float2 *__restrict__ pairs, float *__restrict__ out,
-                              Slot *ring, int *cons, float *ll_out) {
+                              Slot *ring, int ring_size, int *cons, float *ll_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int Tn = L.Tn, Un = L.Un, st = L.stride;
     const int T1 = Tn - 1, U1 = Un - 1;
     const float2 *pr = pairs + L.base;
     float *o = out + L.base;
     const int cols_per_pass = 32 * nwarps;
+    const int ring_used = min(ring_size, Tn);
 
     for (int col0 = 0; col0 < Un; col0 += cols_per_pass) {
         if (col0 > 0) __syncthreads();  // previous pass complete (its last column is our left boundary)
         // reset ring tags / consumer counters for this pass
-        for (int k = threadIdx.x; k < nwarps * kRing; k += blockDim.x) ring[k].row = -1;
-        if (threadIdx.x < nwarps) cons[threadIdx.x] = 0;
+        if (Un - col0 > 32) {
+            for (int k = threadIdx.x; k < nwarps * ring_used; k += blockDim.x)
+                ring[(size_t)(k / ring_used) * ring_size + (k % ring_used)].row = -1;
+            if (threadIdx.x < nwarps) cons[threadIdx.x] = 0;
+        }
         __syncthreads();
 
         const int wcol = col0 + 32 * warp;
         if (wcol >= Un) continue;  // warp idle in this pass (still takes part in the barriers above)
-        const int j = wcol + lane;
-        const bool col_ok = j < Un;
+        Sweep S;
+        S.pr = pr; S.o = o;
+        S.Tn = Tn; S.Un = Un; S.st = st; S.T1 = T1; S.U1 = U1;
+        S.lane = lane;
+        S.j = wcol + lane;
+        S.col_ok = S.j < Un;
         const int active = min(32, Un - wcol);
-        const int nsteps = Tn + active - 1;
-        const bool has_next = (wcol + 32 < Un) && (warp + 1 < nwarps);  // we publish our lane-31 column
-        const bool from_ring = warp > 0;                                // lane 0's left neighbour is in the ring
-        const bool from_gmem = (warp == 0 && col0 > 0);                 // ... or in global memory (previous pass)
-        Slot *ring_in = ring + (size_t)(warp - 1) * kRing;
-        Slot *ring_out = ring + (size_t)warp * kRing;
+        S.nsteps = Tn + active - 1;
+        S.publish = (wcol + 32 < Un) && (warp + 1 < nwarps);   // lane 31's column feeds the next warp
+        S.ring_in = ring + (size_t)(warp > 0 ? warp - 1 : 0) * ring_size;
+        S.ring_out = ring + (size_t)warp * ring_size;
+        S.cons_self = cons + warp;
+        S.cons_next = cons + min(warp + 1, nwarps - 1);
+        S.ring_mask = ring_size - 1;
+        S.backpressure = Tn > ring_size;
+        S.override0 = false;
 
         // Exact mode, column 0: the reference builds it with a 32-wide Kogge-Stone scan per tile
         // plus the tile's base value (core.cu:92-110 / :197-215); reproduce that summation order
@@ -228,102 +378,16 @@ __device__ void wavefront_dir(const Lattice &L, const float2 *__restrict__ pairs
                 base = __shfl_sync(0xffffffffu, v, 31);
             }
             __syncwarp();
+            S.override0 = true;
         }
 
-        float val = kNegInf;      // val[i-1, j] (own column, previous row); -inf drops the skip term on row 0
-        int cons_seen = 0;        // producer-side cache of the next warp's consumed-row counter
-        float wbA[kPrefetch], wlA[kPrefetch], bndA[kPrefetch];
-        float wbB[kPrefetch], wlB[kPrefetch], bndB[kPrefetch];
+        float val;
+        if (warp > 0) val = sweep_warp<KIND, BETA, kLeftRing>(S);
+        else if (col0 > 0 || col0_scan) val = sweep_warp<KIND, BETA, kLeftMem>(S);
+        else val = sweep_warp<KIND, BETA, kLeftNone>(S);
 
-        // log-probs (and memory-resident boundary values) for steps [s0, s0+kPrefetch)
-        auto load_chunk = [&](float (&wb)[kPrefetch], float (&wl)[kPrefetch], float (&bnd)[kPrefetch], int s0) {
-#pragma unroll
-            for (int k = 0; k < kPrefetch; ++k) {
-                const int i = s0 + k - lane;
-                wb[k] = 0.0f;
-                wl[k] = 0.0f;
-                bnd[k] = kNegInf;
-                if (col_ok && i >= 0 && i < Tn) {
-                    if (BETA) {
-                        const float2 w = pr[(int64_t)(T1 - i) * st + (U1 - j)];
-                        wb[k] = w.x;
-                        wl[k] = w.y;
-                    } else {
-                        if (i >= 1) wb[k] = pr[(int64_t)(i - 1) * st + j].x;
-                        if (j >= 1) wl[k] = pr[(int64_t)i * st + (j - 1)].y;
-                    }
-                    if (lane == 0) {
-                        if (from_gmem) bnd[k] = __ldcg(&o[BETA ? ((int64_t)(T1 - i) * st + (U1 - (j - 1))) : ((int64_t)i * st + (j - 1))]);
-                        if (col0_scan && i >= 1) bnd[k] = __ldcg(&o[BETA ? ((int64_t)(T1 - i) * st + U1) : ((int64_t)i * st)]);
-                    }
-                }
-            }
-        };
-
-        auto run_chunk = [&](const float (&wb)[kPrefetch], const float (&wl)[kPrefetch], const float (&bnd)[kPrefetch], int s0) {
-#pragma unroll
-            for (int k = 0; k < kPrefetch; ++k) {
-                const int s = s0 + k;
-                if (s >= nsteps) break;           // warp-uniform
-                const int i = s - lane;
-                float left = __shfl_up_sync(0xffffffffu, val, 1);
-                if (lane == 0) {
-                    left = kNegInf;
-                    if (from_gmem) left = bnd[k];
-                }
-                if (from_ring && s < Tn) {        // warp-uniform: lane 0's row s needs the boundary value
-                    Slot sl = ld_slot(&ring_in[s & (kRing - 1)]);
-                    while (sl.row != s) {
-                        __nanosleep(20);
-                        sl = ld_slot(&ring_in[s & (kRing - 1)]);
-                    }
-                    if (lane == 0) {
-                        left = sl.val;
-                        st_vol_s32(&cons[warp], s + 1);
-                    }
-                }
-                const bool act = col_ok && i >= 0 && i < Tn;
-                if (act) {
-                    float v;
-                    if (i == 0 && j == 0) {
-                        v = BETA ? wb[k] : 0.0f;                      // beta[T-1,U-1] = blank there; alpha[0,0] = 0
-                    } else if (col0_scan && lane == 0) {
-                        v = bnd[k];                                   // column 0 from the scan pre-pass
-                    } else {
-                        const float skip = val + wb[k];
-                        const float emit = left + wl[k];
-                        if (i == 0) v = emit;                         // first row: label transitions only (core.cu:80-90)
-                        else if (j == 0) v = skip;                    // first column: blank transitions only
-                        else v = lse<KIND>(skip, emit);
-                    }
-                    val = v;
-                    o[BETA ? ((int64_t)(T1 - i) * st + (U1 - j)) : ((int64_t)i * st + j)] = v;
-                }
-                if (has_next && s >= 31 && s - 31 < Tn) {             // warp-uniform: lane 31 finished row s-31
-                    const int row = s - 31;
-                    if (row - kRing >= cons_seen) {                   // ring slot still unread? wait for the consumer
-                        int c = ld_vol_s32(&cons[warp + 1]);
-                        while (row - kRing >= c) {
-                            __nanosleep(20);
-                            c = ld_vol_s32(&cons[warp + 1]);
-                        }
-                        cons_seen = c;
-                    }
-                    if (lane == 31) st_slot(&ring_out[row & (kRing - 1)], val, row);
-                }
-            }
-        };
-
-        // double-buffered: the loads of the next chunk are in flight while this chunk's chain runs
-        load_chunk(wbA, wlA, bndA, 0);
-        for (int s0 = 0; s0 < nsteps; s0 += 2 * kPrefetch) {
-            load_chunk(wbB, wlB, bndB, s0 + kPrefetch);
-            run_chunk(wbA, wlA, bndA, s0);
-            load_chunk(wbA, wlA, bndA, s0 + 2 * kPrefetch);
-            run_chunk(wbB, wlB, bndB, s0 + kPrefetch);
-        }
         // the thread that owns the last cell reports the log-likelihood seen from this direction
-        if (j == U1 && ll_out != nullptr) {
+        if (S.j == U1 && ll_out != nullptr) {
             // alpha side: alpha[T-1,U-1] + blank[T-1,U-1] (core.cu:346) ; beta side: beta[0,0]
             *ll_out = BETA ? val : val + pr[(int64_t)T1 * st + U1].x;
         }
@@ -333,21 +397,21 @@ __device__ void wavefront_dir(const Lattice &L, const float2 *__restrict__ pairs
 // grid (2, N) with cluster (2,1,1): rank 0 = alpha, rank 1 = beta (beta_only: grid (1,N), no cluster).
 // ws_ll: (2,N) floats {alpha-side ll, beta-side ll}; bad: (N) ints (1 = mismatch guard fired).
 template <int KIND>
-__global__ void __launch_bounds__(512) k_wavefront(Problem p, const float2 *__restrict__ pairs,
+__global__ void __launch_bounds__(512, 1) k_wavefront(Problem p, const float2 *__restrict__ pairs,
                                                     float *__restrict__ alphas, float *__restrict__ betas,
                                                     float *__restrict__ ws_ll, int *__restrict__ bad,
-                                                    float *__restrict__ costs, int beta_only, int guard) {
+                                                    float *__restrict__ costs, int beta_only, int guard, int ring_size) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nwarps = blockDim.x >> 5;
     Slot *ring = reinterpret_cast<Slot *>(smem_raw);
-    int *cons = reinterpret_cast<int *>(smem_raw + sizeof(Slot) * (size_t)nwarps * kRing);
+    int *cons = reinterpret_cast<int *>(smem_raw + sizeof(Slot) * (size_t)nwarps * ring_size);
     const int n = blockIdx.y;
     const bool is_beta = beta_only || (blockIdx.x == 1);
     const Lattice L = get_lattice(p, n);
     float *ll = ws_ll + (is_beta ? p.N : 0) + n;
     if (L.ok) {
-        if (is_beta) wavefront_dir<KIND, true>(L, pairs, betas, ring, cons, ll);
-        else wavefront_dir<KIND, false>(L, pairs, alphas, ring, cons, ll);
+        if (is_beta) wavefront_dir<KIND, true>(L, pairs, betas, ring, ring_size, cons, ll);
+        else wavefront_dir<KIND, false>(L, pairs, alphas, ring, ring_size, cons, ll);
     }
     if (!beta_only) {
         // alpha and beta CTAs of a lattice meet here; release/acquire orders the ll writes.
@@ -458,10 +522,22 @@ cudaError_t launch_gather(cudaStream_t s, const Problem &p, const float *lp, con
 template <int KIND>
 static cudaError_t launch_wavefront_kind(cudaStream_t s, const Problem &p, const float2 *pairs, float *alphas,
                                          float *betas, float *ws_ll, int *bad, float *costs, int beta_only,
-                                         int guard, int u_hint) {
-    int nwarps = (u_hint + 31) / 32;
+                                         int guard, int t_hint, int u_hint) {
+    // warps per CTA: one per 32 lattice columns, at most 16 (more columns -> column passes)
+    int nwarps = (u_hint > 0 ? u_hint + 31 : 512) / 32;
     nwarps = max(1, min(nwarps, 16));
-    const size_t smem = sizeof(Slot) * (size_t)nwarps * kRing + sizeof(int) * nwarps;
+    // boundary ring: one slot per row when it fits (no back-pressure), else a 128-slot ring
+    int ring = 128;
+    if (nwarps > 1 && t_hint > 0) {
+        while (ring < t_hint && (size_t)ring * 2 * nwarps * sizeof(Slot) <= 160 * 1024) ring *= 2;
+    }
+    const size_t smem = sizeof(Slot) * (size_t)nwarps * ring + sizeof(int) * nwarps;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_wavefront<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(beta_only ? 1 : 2, p.N, 1);
     cfg.blockDim = dim3(32 * nwarps, 1, 1);
@@ -475,19 +551,20 @@ static cudaError_t launch_wavefront_kind(cudaStream_t s, const Problem &p, const
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     count_launch();
-    return cudaLaunchKernelEx(&cfg, k_wavefront<KIND>, p, pairs, alphas, betas, ws_ll, bad, costs, beta_only, guard);
+    return cudaLaunchKernelEx(&cfg, k_wavefront<KIND>, p, pairs, alphas, betas, ws_ll, bad, costs, beta_only, guard,
+                              ring);
 }
 
 cudaError_t launch_wavefront(cudaStream_t s, int kind, const Problem &p, const float2 *pairs, float *alphas,
                              float *betas, float *ws_ll, int *bad, float *costs, int beta_only, int guard,
-                             int u_hint) {
+                             int t_hint, int u_hint) {
     switch (kind) {
         case kExactDense:
-            return launch_wavefront_kind<kExactDense>(s, p, pairs, alphas, betas, ws_ll, bad, costs, beta_only, guard, u_hint);
+            return launch_wavefront_kind<kExactDense>(s, p, pairs, alphas, betas, ws_ll, bad, costs, beta_only, guard, t_hint, u_hint);
         case kExactCompact:
-            return launch_wavefront_kind<kExactCompact>(s, p, pairs, alphas, betas, ws_ll, bad, costs, beta_only, guard, u_hint);
+            return launch_wavefront_kind<kExactCompact>(s, p, pairs, alphas, betas, ws_ll, bad, costs, beta_only, guard, t_hint, u_hint);
         default:
-            return launch_wavefront_kind<kFast>(s, p, pairs, alphas, betas, ws_ll, bad, costs, beta_only, guard, u_hint);
+            return launch_wavefront_kind<kFast>(s, p, pairs, alphas, betas, ws_ll, bad, costs, beta_only, guard, t_hint, u_hint);
     }
 }
 
