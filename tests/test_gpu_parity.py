@@ -327,3 +327,52 @@ def test_exact_mode_is_bit_identical_to_reference_gather_and_compact(w, ref, sha
     br = ref.rnnt_loss_compact_backward(go, gr, cumlen, lr, V, blank)
     bm = w._C.rnnt_loss_compact_backward(go, gm, cumlen, lm, V, blank)
     assert torch.equal(bm, br)
+
+
+# ------------------------------------------------------------------ drop-in at the C-ABI level
+@pytest.fixture(scope="module")
+def compat():
+    from oracle import build_ref
+    return build_ref.load_compat()
+
+
+@pytest.mark.parametrize("name", ["test_one_to_many", "test_one_to_empty", "test_forward_single", "test_forward_batch"])
+def test_reference_binding_on_our_c_abi_golden(w, compat, name):
+    """The reference's UNMODIFIED pytorch_binding/binding.cpp linked against librnnt_b200.so
+    (run_warp_rnnt & co, core.h:29-60) reproduces the reference's own test vectors."""
+    if compat is None:
+        pytest.skip("oracle/_ref/warp_rnnt_compat_C.so not present")
+    c = golden_case(name)
+    costs, grads = compat.rnnt_loss(cu(c["lp"]), cu(c["ys"]), cu(c["xn"]), cu(c["yn"]))
+    np.testing.assert_array_almost_equal(costs.cpu().numpy(), c["costs"], decimal=6)
+    np.testing.assert_array_almost_equal(grads.cpu().numpy(), c["grads"], decimal=6)
+
+
+def test_reference_binding_on_our_c_abi_all_layouts(w, compat, ref):
+    if compat is None or ref is None:
+        pytest.skip("oracle/_ref extensions not present")
+    N, T, U, V, blank, lam = 4, 45, 37, 11, 3, 0.2
+    lp, ys, xn, yn = make_inputs(N, T, U, V, seed=77, random_lengths=True, blank=blank)
+    w.set_lse_mode("exact")                      # compat ABI uses the process-wide LSE mode
+    args = (cu(lp), cu(ys), cu(xn), cu(yn))
+    cr, gr = ref.rnnt_loss(*args, blank=blank, fastemit_lambda=lam)
+    cm, gm = compat.rnnt_loss(*args, blank=blank, fastemit_lambda=lam)
+    assert torch.equal(cm, cr) and torch.equal(gm, gr)
+    g = gather_np(lp, ys, blank)
+    gargs = (cu(g), cu(ys), cu(xn), cu(yn))
+    cr, gr = ref.rnnt_loss(*gargs, blank=-1, fastemit_lambda=lam)
+    cm, gm = compat.rnnt_loss(*gargs, blank=-1, fastemit_lambda=lam)
+    assert torch.equal(cm, cr) and torch.equal(gm, gr)
+    xs_c, ys_c = to_compact(lp, ys, xn, yn)
+    cargs = (cu(xs_c), cu(ys_c), cu(xn), cu(yn))
+    cr, gr, lr = ref.rnnt_loss_compact(*cargs, blank=blank, fastemit_lambda=lam)
+    cm, gm, lm = compat.rnnt_loss_compact(*cargs, blank=blank, fastemit_lambda=lam)
+    used = lr != blank
+    assert torch.equal(cm, cr) and torch.equal(lm, lr) and torch.equal(gm[:, 0], gr[:, 0])
+    assert torch.equal(gm[:, 1][used], gr[:, 1][used])
+    cumlen = torch.cumsum(cu(xn) * (cu(yn) + 1), dim=0, dtype=torch.int32)
+    go = torch.linspace(0.5, 1.5, N).cuda()
+    br = ref.rnnt_loss_compact_backward(go, gr, cumlen, lr, V, blank)
+    bm = compat.rnnt_loss_compact_backward(go, gm, cumlen, lm, V, blank)
+    assert torch.equal(bm, br)
+    w.set_lse_mode("auto")

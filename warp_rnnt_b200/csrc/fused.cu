@@ -51,6 +51,30 @@ __device__ __forceinline__ void st_fslot(uint32_t addr, float v, int row) {
     asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "f"(v), "r"(row) : "memory");
 }
 
+// L2 residency control (B200: 126 MB L2).  The dense gradient slab is zero-filled while the
+// wavefront runs and patched afterwards; the patch is a partial-sector write, so it must still HIT
+// in L2 or ECC forces a DRAM read-modify-write per touched sector.  Filled lines are therefore
+// stored evict_last (256-bit STG.E.ELL2.256), and the one-pass log-prob gather is loaded
+// evict_first so that it cannot displace them.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float ldg_hint(const float *ptr, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float2 ldg_hint2(const float2 *ptr, uint64_t pol) {
+    float2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stg_zero256_evict_last(float *ptr) {
+    asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(ptr), "r"(0) : "memory");
+}
+
 struct FusedArgs {
     const float *lp;        // dense (N,T,U,V) or, pairs_in, (N,T,U,2)
     const int *labels;      // (N,U-1)
@@ -241,6 +265,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     if (ok && warp < GW) {
         const int cells = Tn * Un;
         const float inv = 1.0f / (float)Un;
+        const uint64_t pol_first = policy_evict_first();
         constexpr int G = 4;                                    // cells per thread per pass: all loads first
         for (int cb = tid; cb < cells; cb += gthreads * G) {
             float vb[G], vl[G];
@@ -257,13 +282,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
                 idx[g] = in ? (t + kPad) * W + u + 1 : -1;
                 vl[g] = kBigF;
                 if (A.pairs_in) {
-                    const float2 w2 = __ldg(reinterpret_cast<const float2 *>(A.lp) + cell);
+                    const float2 w2 = ldg_hint2(reinterpret_cast<const float2 *>(A.lp) + cell, pol_first);
                     vb[g] = w2.x;
                     if (u < U1) vl[g] = w2.y;
                 } else {
                     const float *row = A.lp + cell * V;
-                    vb[g] = __ldg(row + A.blank);
-                    if (u < U1) vl[g] = __ldg(row + s_lab[u]);
+                    vb[g] = ldg_hint(row + A.blank, pol_first);
+                    if (u < U1) vl[g] = ldg_hint(row + s_lab[u], pol_first);
                 }
             }
 #pragma unroll
@@ -305,15 +330,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         }
     }
     if (MODE == 0) {
-        // zero-fill rows [t0,t1) of this lattice's slab: floats [f0,f1); 16 KB chunks handed out by s_next
+        // zero-fill rows [t0,t1) of this lattice's slab: floats [f0,f1); 32 KB chunks handed out by
+        // s_next; 256-bit evict_last stores on the 32-byte aligned interior
         const int64_t f0 = (slab + (int64_t)t0 * U) * V, f1 = (slab + (int64_t)t1 * U) * V;
         float *g = A.grads;
-        const bool vec = ((reinterpret_cast<uintptr_t>(g) & 15u) == 0);
-        const int64_t a0 = vec ? min(f1, (f0 + 3) & ~(int64_t)3) : f1;
-        const int64_t a1 = vec ? max(a0, f1 & ~(int64_t)3) : f1;
-        constexpr int kChunk = 4096;                            // floats per chunk
+        const bool vec = ((reinterpret_cast<uintptr_t>(g) & 31u) == 0);
+        const int64_t a0 = vec ? min(f1, (f0 + 7) & ~(int64_t)7) : f1;
+        const int64_t a1 = vec ? max(a0, f1 & ~(int64_t)7) : f1;
+        constexpr int kChunk = 8192;                            // floats per chunk
         const int64_t nchunks = (a1 - a0 + kChunk - 1) / kChunk;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         for (;;) {
             int c = 0;
             if (lane == 0) c = atomicAdd(&s_next, 1);
@@ -322,9 +347,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
             const int64_t b = a0 + (int64_t)c * kChunk;
             const int64_t e = min(a1, b + kChunk);
 #pragma unroll 4
-            for (int64_t f = b + 4 * lane; f < e; f += 128) *reinterpret_cast<float4 *>(g + f) = z;
+            for (int64_t f = b + 8 * lane; f < e; f += 256) stg_zero256_evict_last(g + f);
         }
-        if (warp == kFusedThreads / 32 - 1) {                   // unaligned head / tail (<= 3 floats each, or all if !vec)
+        if (warp == kFusedThreads / 32 - 1) {                   // unaligned head / tail (<= 7 floats each, or all if !vec)
             for (int64_t f = f0 + lane; f < a0; f += 32) g[f] = 0.0f;
             for (int64_t f = a1 + lane; f < f1; f += 32) g[f] = 0.0f;
         }
