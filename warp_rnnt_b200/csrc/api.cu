@@ -50,9 +50,9 @@ static int g_path = -1;
 static bool want_fused(int N, int T, int U, FusedPlan *plan) {
     if (g_path < 0) {
         const char *e = getenv("RNNT_B200_PATH");
-        g_path = (e && !strcmp(e, "general")) ? 2 : (e && !strcmp(e, "fused")) ? 1 : 0;
+        g_path = (e && !strcmp(e, "general")) ? 2 : (e && !strcmp(e, "diag")) ? 4 : (e && !strcmp(e, "fused")) ? 1 : 0;
     }
-    if (g_path == 2) return false;
+    if (g_path >= 2) return false;
     return fused_plan(N, T, U, plan);
 }
 
@@ -92,6 +92,61 @@ static bool dense_args_ok(int N, int T, int U, int V) {
     if ((int64_t)N * T * U >= (int64_t)1 << 31) return false;   // cell ids are 32-bit in the emit kernel
     if (V >= (1 << 22)) return false;
     return true;
+}
+
+// RNNT_B200_PATH=diag selects the diagonal-major general path (diag.cu) for every shape it supports.
+// It is verified by the same tests (bit-identical in exact mode) but NOT the default: measured on
+// B200 at cfg 4 it is slower end to end than the row-major path (3.28 ms vs 2.50 ms) -- its
+// single-warp wavefront is 1.6x faster (535 vs 836 us) but the scattered staging writes of
+// k_diag_gather / k_diag_grads cost more than that.  See DESIGN.md section 8.
+static bool want_diag(int N, int t_max, int u_max, DiagPlan *plan) {
+    if (g_path < 0) { FusedPlan f; (void)want_fused(1, 1, 1, &f); }
+    if (g_path != 4) return false;
+    return diag_plan(N, t_max, u_max, plan);
+}
+
+// Diagonal-major general path.  Scratch comes from the stream-ordered allocator (its size depends
+// on T and U, which rnnt_b200_workspace_bytes(cells, N) cannot see).  pg_out: (cells,2) gradients
+// or nullptr (costs only); when dense_out != nullptr the gradients are expanded to (cells,V).
+static int run_diag(cudaStream_t s, int kind, const Problem &p, const DiagPlan &plan, const float *lp,
+                    const int *labels, int V, int blank, int pairs_in, int64_t *loc, float *costs, float2 *pg_out,
+                    float *dense_out, const float *scale, int64_t cells, float lam, int guard) {
+    const size_t llb = align_up(sizeof(float) * 2 * p.N, 256), badb = align_up(sizeof(int) * p.N, 256);
+    const size_t pgb = (dense_out && !pg_out) ? align_up(sizeof(float2) * (size_t)cells, 256) : 0;
+    {
+        // keep freed scratch in the stream-ordered pool instead of returning it to the OS at every
+        // synchronisation (the default release threshold is 0, which makes each call re-map ~1 GB)
+        static bool pool_ready = false;
+        if (!pool_ready) {
+            int dev = 0;
+            cudaMemPool_t pool;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t thr = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+            pool_ready = true;
+        }
+    }
+    char *tmp = nullptr;
+    if (cudaMallocAsync((void **)&tmp, align_up(plan.scratch_bytes, 256) + llb + badb + pgb, s) != cudaSuccess) {
+        cudaGetLastError();
+        return RNNT_STATUS_WORKSPACE_TOO_SMALL;
+    }
+    float *ll = (float *)(tmp + align_up(plan.scratch_bytes, 256));
+    int *bad = (int *)((char *)ll + llb);
+    float2 *pg = pg_out ? pg_out : (dense_out ? (float2 *)((char *)bad + badb) : nullptr);
+    int status = RNNT_STATUS_SUCCESS;
+    if (launch_diag_forward(s, kind, p, plan, tmp, lp, labels, V, blank, pairs_in, loc, ll, guard ? bad : nullptr, costs,
+                            pg, lam, guard) != cudaSuccess)
+        status = RNNT_STATUS_WARP_FAILED;
+    if (!status && dense_out) {
+        ExpandSrc src = {};
+        src.pg = pg; src.scale = scale; src.labels = labels; src.label_adds = 0;
+        Problem pd = p;
+        if (launch_expand(s, pd, src, dense_out, cells, V, blank) != cudaSuccess) status = RNNT_STATUS_GRADS_BLANK_FAILED;
+    }
+    cudaFreeAsync(tmp, s);
+    return status;
 }
 
 #define RNNT_TRY(expr, code)                                            \
@@ -150,6 +205,12 @@ int rnnt_b200_loss_dense(void *stream, void *workspace, size_t workspace_bytes, 
                  RNNT_STATUS_WARP_FAILED);
         return RNNT_STATUS_SUCCESS;
     }
+    DiagPlan dplan;
+    if (want_diag(N, T, U, &dplan)) {
+        Problem pd = {xn, yn, nullptr, nullptr, N, T, U, 0};
+        return run_diag(s, resolve_kind(lse_mode, false), pd, dplan, log_probs, labels, V, blank, 0, nullptr, costs,
+                        nullptr, grads, grad_scale, cells, fastemit_lambda, 1);
+    }
     const Workspace w = carve(workspace, cells, N);
     if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
     Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
@@ -182,6 +243,12 @@ int rnnt_b200_loss_pairs(void *stream, void *workspace, size_t workspace_bytes, 
                  RNNT_STATUS_WARP_FAILED);
         return RNNT_STATUS_SUCCESS;
     }
+    DiagPlan dplan;
+    if (want_diag(N, T, U, &dplan)) {
+        Problem pd = {xn, yn, nullptr, nullptr, N, T, U, 0};
+        return run_diag(s, resolve_kind(lse_mode, false), pd, dplan, pairs, nullptr, 2, 0, 1, nullptr, costs,
+                        reinterpret_cast<float2 *>(pair_grads), nullptr, nullptr, cells, fastemit_lambda, 1);
+    }
     const Workspace w = carve(workspace, cells, N);
     if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
     Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
@@ -210,6 +277,12 @@ int rnnt_b200_gather_forward(void *stream, void *workspace, size_t workspace_byt
                               reinterpret_cast<float2 *>(pair_grads), nullptr, N, T, U, V, blank, fastemit_lambda, 0, 1),
                  RNNT_STATUS_WARP_FAILED);
         return RNNT_STATUS_SUCCESS;
+    }
+    DiagPlan dplan;
+    if (want_diag(N, T, U, &dplan)) {
+        Problem pd = {xn, yn, nullptr, nullptr, N, T, U, 0};
+        return run_diag(s, resolve_kind(lse_mode, false), pd, dplan, log_probs, labels, V, blank, 0, nullptr, costs,
+                        reinterpret_cast<float2 *>(pair_grads), nullptr, nullptr, cells, fastemit_lambda, 1);
     }
     const Workspace w = carve(workspace, cells, N);
     if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
@@ -253,6 +326,12 @@ int rnnt_b200_compact_forward(void *stream, void *workspace, size_t workspace_by
     if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
     RNNT_TRY(launch_prefix(s, xn, yn, N, w.mem_pref, w.lab_pref, totals ? totals : w.totals), RNNT_STATUS_GATHER_FAILED);
     Problem p = {xn, yn, w.mem_pref, w.lab_pref, N, 0, 0, 1};
+    DiagPlan dplan;
+    if (max_T > 0 && max_U > 0 && want_diag(N, max_T, max_U, &dplan)) {
+        // no mismatch guard in the compact reference (core_compact.cu:347-358)
+        return run_diag(s, resolve_kind(lse_mode, true), p, dplan, xs, ys, V, blank, 0, loc, costs,
+                        reinterpret_cast<float2 *>(pair_grads), nullptr, nullptr, STU, fastemit_lambda, 0);
+    }
     RNNT_TRY(launch_gather(s, p, xs, ys, V, blank, w.pairs, loc, STU), RNNT_STATUS_GATHER_FAILED);
     // no mismatch guard in the compact reference (core_compact.cu:347-358)
     RNNT_TRY(launch_wavefront(s, resolve_kind(lse_mode, true), p, w.pairs, w.alphas, w.betas, w.ll, w.bad, costs,

@@ -105,7 +105,8 @@ k_expand(Problem p, ExpandSrc src, float *__restrict__ out, int64_t cells, int V
             const float2 g = s_g[row];
             const int lab = s_lab[row];
             float x = (v == blank) ? g.x : 0.0f;
-            if (v == lab) x = (MODE == 1 && src.label_adds) ? x + g.y : g.y;
+            // override mode: a zero label gradient marks "no label transition here" (padded labels may equal blank)
+            if (v == lab) x = (MODE == 1 && src.label_adds) ? x + g.y : ((MODE == 1 && g.y == 0.0f) ? x : g.y);
             return x;
         };
         int64_t a0 = vec_ok ? min(f1, (f0 + 3) & ~(int64_t)3) : f1;

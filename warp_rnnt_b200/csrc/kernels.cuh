@@ -44,4 +44,11 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
                          const float *scale, int N, int T, int U, int V, int blank, float lam, int pairs_in,
                          int guard);
 
+// diag.cu -- general path on diagonal-major staged operands (any T, U <= 512)
+struct DiagPlan { int C, Wd, nd, t_cap; size_t smem; int64_t plane; size_t scratch_bytes; };
+bool diag_plan(int N, int t_max, int u_max, DiagPlan *plan);
+cudaError_t launch_diag_forward(cudaStream_t s, int kind, const Problem &p, const DiagPlan &plan, void *scratch,
+                                const float *lp, const int *labels, int V, int blank, int pairs_in, int64_t *loc,
+                                float *ws_ll, int *bad, float *costs, float2 *pg, float fastemit_lambda, int guard);
+
 }  // namespace rnnt
