@@ -188,20 +188,35 @@ def main():
     keep = [None] * R
     torch.cuda.synchronize()
 
+    pending = []                                        # in-flight scalar all-reduces (world > 1)
+
     def step(i):
         s = sets[i % R]
         costs, grads = w._C.rnnt_loss(s[0], s[1], s[2], s[3])
         keep[i % R] = (costs, grads)
         if world > 1:
+            # the one collective of the sharded path: 1 float, issued asynchronously so that step i's
+            # all-reduce (NCCL stream) overlaps step i+1's kernel; the value is only consumed one step
+            # later (logging / optimizer in a real loop), which is when we wait on it
             loss = costs.sum()
-            dist.all_reduce(loss)                       # the one collective of the sharded path
-            return loss
+            pending.append((dist.all_reduce(loss, async_op=True), loss))
+            if len(pending) > 1:
+                pending.pop(0)[0].wait()
         return costs
+
+    def drain():
+        while pending:
+            pending.pop(0)[0].wait()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # prime the caching allocator: R live outputs + the one being produced must all exist before
+    # the timed region, or a cudaMalloc (~1 ms) lands inside it
+    for i in range(R + 2):
+        step(i)
     for i in range(args.warmup):
         step(i)
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -211,6 +226,7 @@ def main():
     e0.record()
     for i in range(args.steps):
         step(args.warmup + i)
+    drain()                                             # every all-reduce of the K steps has completed
     e1.record()
     torch.cuda.synchronize()
     launches = w._C.launch_count() - launches0
@@ -222,6 +238,22 @@ def main():
         dist.barrier()
     ms_per_step = ms / args.steps
     value = N * world * args.steps / (ms * 1e-3)
+
+    # the opt-in short LSE chain, same protocol (extra information; the headline is the default mode)
+    fast_ms = None
+    if world == 1 and args.lse == "auto":
+        w.set_lse_mode("fast")
+        for i in range(3):
+            step(i)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(args.steps):
+            step(3 + i)
+        f1.record()
+        torch.cuda.synchronize()
+        fast_ms = f0.elapsed_time(f1) / args.steps
+        w.set_lse_mode("auto")
 
     # ---- end to end through the public API, host buffers
     ke = args.e2e_steps or min(args.steps, 20)
@@ -276,7 +308,8 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %s" % (args.workload, desc), "lattices_per_gpu": N, "T": T, "U": U, "V": V,
                    "global_batch": N * world, "parallelism": "batch-sharded x%d, scalar-loss all-reduce" % world,
-                   "lse_mode": args.lse, "l2_protocol": "%d rotating input sets + %d live outputs (%.0f MB) > L2" % (R, R, R * per_set / 1e6),
+                   "lse_mode": args.lse + (" (= exact: results bit-identical to the reference kernels)" if args.lse == "auto" else ""),
+                   "l2_protocol": "%d rotating input sets + %d live outputs (%.0f MB) > L2" % (R, R, R * per_set / 1e6),
                    "timed_call": "_C.rnnt_loss (loss + dense grads, one fused kernel)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": balg, "peak_source": peak_src,
@@ -287,6 +320,11 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if fast_ms is not None:
+        out["lse_fast"] = {"ms_per_step": fast_ms, "value": N / (fast_ms * 1e-3), "unit": "lattices/s",
+                           "roofline_frac": balg / (fast_ms * 1e-3) / 1e9 / peak,
+                           "note": "opt-in RNNT_LSE_FAST (fp32-noise-level deviation from the reference, <= ~1e-4 on gradients); "
+                                   "the headline value uses the default mode, which is bit-identical to the reference"}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_oracle_rate(N, T, U, V)
     print(json.dumps(out), flush=True)
@@ -351,6 +389,8 @@ def run_reference(args, rank, world, N, T, U, V, desc, have_cuda):
 
     sampler = ClockSampler(dev.index or 0)
     sampler.start()
+    for i in range(R + 2):                              # prime the caching allocator (see main())
+        step(i)
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()

@@ -51,7 +51,7 @@ typedef enum {
  *                    costs and gradients are bit-identical to the reference kernels.
  *   RNNT_LSE_FAST  : max + ln2*lg2.approx(1 + ex2.approx(d*log2e)); ~3x shorter dependent chain,
  *                    |error| < 4e-7 per step (measured against the fp64 oracle in tests/).
- *   RNNT_LSE_AUTO  : the library's per-shape choice (documented in DESIGN.md). */
+ *   RNNT_LSE_AUTO  : the library default = RNNT_LSE_EXACT (parity first). */
 typedef enum { RNNT_LSE_AUTO = 0, RNNT_LSE_EXACT = 1, RNNT_LSE_FAST = 2 } rnntLseMode_t;
 
 /* Process-wide default for calls that do not pass a mode (the compat ABI (B)); initialised from

@@ -33,7 +33,12 @@ def stalls(rep):
     hdr, data = rows[1], rows[2:]
     ci = {h: i for i, h in enumerate(hdr)}
     st = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-    agg = {s: sum(float(r[ci[s]] or 0) for r in data if len(r) > ci[s]) for s in st}
+    def num(x):
+        try:
+            return float(x or 0)
+        except ValueError:      # a repeated header row (several kernels in one report)
+            return 0.0
+    agg = {s: sum(num(r[ci[s]]) for r in data if len(r) > ci[s]) for s in st}
     tot = sum(agg.values()) or 1.0
     return {k: round(100 * v / tot, 1) for k, v in sorted(agg.items(), key=lambda x: -x[1]) if v > 0}
 

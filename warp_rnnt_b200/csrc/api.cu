@@ -34,13 +34,16 @@ static int default_lse_mode() {
     return m;
 }
 
-// AUTO policy (DESIGN.md "numerics"): the exact chain is ~3x longer per anti-diagonal; it only
-// matters where the wavefront is exposed.  AUTO = fast; callers that want bit-parity with the
-// reference kernels ask for RNNT_LSE_EXACT (or set RNNT_B200_LSE=exact).
+// AUTO policy (DESIGN.md "numerics"): AUTO = exact, i.e. results are bit-identical to the reference
+// kernels unless the caller opts out.  Parity is the first gate: at BASELINE cfg 2 the fast flavour
+// differs from the reference by up to 1.2e-4 on a gradient (pure fp32 noise -- the reference itself is
+// 1.25e-4 away from fp64 there), which is outside the stated 1e-4.  The exact chain is ~2x longer per
+// anti-diagonal; it costs ~10 us at cfg 2 and nothing measurable where the dense write dominates
+// (cfg 3-5).  RNNT_LSE_FAST / RNNT_B200_LSE=fast selects the short chain.
 static int resolve_kind(int lse_mode, bool compact) {
     if (lse_mode == RNNT_LSE_AUTO) lse_mode = default_lse_mode();
-    if (lse_mode == RNNT_LSE_EXACT) return compact ? kExactCompact : kExactDense;
-    return kFast;
+    if (lse_mode == RNNT_LSE_FAST) return kFast;
+    return compact ? kExactCompact : kExactDense;
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
