@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -152,6 +153,50 @@ static int run_diag(cudaStream_t s, int kind, const Problem &p, const DiagPlan &
     return status;
 }
 
+// Internal streams for the pipelined general path: one for gathers, one for emits, four
+// high-priority ones for wavefronts (their CTAs are few and long-lived; priority lets them take the
+// SMs that free up at every gather / emit kernel boundary).  Created once per process and device.
+struct Pipeline {
+    static constexpr int kWave = 4, kGroups = 8;
+    cudaStream_t gather_s, expand_s, wave_s[kWave];
+    cudaEvent_t fork, gathered[kGroups], swept[kGroups], join[2 + kWave];
+    int device;
+};
+static bool pipeline_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        // opt-in (RNNT_B200_PIPELINE=1): measured on B200 it does not pay off yet -- cfg 4 2.96 ms
+        // pipelined vs 2.90 ms serial, cfg 5 micro-batch 2.52 vs 2.41 ms
+        const char *e = getenv("RNNT_B200_PIPELINE");
+        on = (e && !strcmp(e, "1")) ? 1 : 0;
+    }
+    return on == 1;
+}
+static Pipeline *get_pipeline() {
+    static Pipeline *pl = nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (pl && pl->device == dev) return pl;
+    if (pl) return nullptr;                      // a second device in one process: keep it simple, no pipeline
+    Pipeline *p = new Pipeline();
+    p->device = dev;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
+    bool ok = cudaStreamCreateWithPriority(&p->gather_s, cudaStreamNonBlocking, lo) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&p->expand_s, cudaStreamNonBlocking, lo) == cudaSuccess;
+    for (int i = 0; i < Pipeline::kWave && ok; ++i)
+        ok = cudaStreamCreateWithPriority(&p->wave_s[i], cudaStreamNonBlocking, hi) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < Pipeline::kGroups && ok; ++i)
+        ok = cudaEventCreateWithFlags(&p->gathered[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&p->swept[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 + Pipeline::kWave && ok; ++i)
+        ok = cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); delete p; return nullptr; }
+    pl = p;
+    return pl;
+}
+
 #define RNNT_TRY(expr, code)                                            \
     do {                                                                \
         cudaError_t e__ = (expr);                                       \
@@ -216,10 +261,57 @@ int rnnt_b200_loss_dense(void *stream, void *workspace, size_t workspace_bytes, 
     }
     const Workspace w = carve(workspace, cells, N);
     if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
+    const int kind = resolve_kind(lse_mode, false);
+    // Large batches of large lattices: software-pipeline lattice groups over internal streams so that the
+    // latency-bound wavefront of group g overlaps the bandwidth-bound gather of g+1 and emit of g-1.
+    const int groups = (grads && N >= 8 && (int64_t)cells * V * 4 >= ((int64_t)512 << 20) && pipeline_enabled())
+                           ? (N >= 32 ? 8 : 4) : 1;
+    if (groups > 1) {
+        Pipeline *pl = get_pipeline();
+        if (pl) {
+            static std::mutex mu;                   // the internal events are shared by all calls
+            std::lock_guard<std::mutex> lock(mu);
+            int status = RNNT_STATUS_SUCCESS;
+            cudaEventRecord(pl->fork, s);
+            cudaStreamWaitEvent(pl->gather_s, pl->fork, 0);
+            cudaStreamWaitEvent(pl->expand_s, pl->fork, 0);
+            for (int i = 0; i < Pipeline::kWave; ++i) cudaStreamWaitEvent(pl->wave_s[i], pl->fork, 0);
+            for (int g = 0; g < groups && !status; ++g) {
+                const int n0 = (int)((int64_t)N * g / groups), n1 = (int)((int64_t)N * (g + 1) / groups);
+                const int ng = n1 - n0;
+                const int64_t c0 = (int64_t)n0 * T * U, cg = (int64_t)ng * T * U;
+                Problem p = {xn + n0, yn + n0, nullptr, nullptr, ng, T, U, 0};
+                const int *lab_g = labels + (int64_t)n0 * (U - 1);
+                cudaStream_t ws = pl->wave_s[g % Pipeline::kWave];
+                if (launch_gather(pl->gather_s, p, log_probs + c0 * V, lab_g, V, blank, w.pairs + c0, nullptr, cg) != cudaSuccess)
+                    status = RNNT_STATUS_GATHER_FAILED;
+                cudaEventRecord(pl->gathered[g], pl->gather_s);
+                cudaStreamWaitEvent(ws, pl->gathered[g], 0);
+                if (!status && launch_wavefront(ws, kind, p, w.pairs + c0, w.alphas + c0, w.betas + c0, w.ll + 2 * n0,
+                                                w.bad + n0, costs + n0, 0, 1, T, U) != cudaSuccess)
+                    status = RNNT_STATUS_WARP_FAILED;
+                cudaEventRecord(pl->swept[g], ws);
+                cudaStreamWaitEvent(pl->expand_s, pl->swept[g], 0);
+                ExpandSrc src = {};
+                src.pairs = w.pairs + c0; src.alphas = w.alphas + c0; src.betas = w.betas + c0; src.bad = w.bad + n0;
+                src.scale = grad_scale ? grad_scale + n0 : nullptr; src.labels = lab_g; src.fastemit_lambda = fastemit_lambda;
+                if (!status && launch_expand(pl->expand_s, p, src, grads + c0 * V, cg, V, blank) != cudaSuccess)
+                    status = RNNT_STATUS_GRADS_BLANK_FAILED;
+            }
+            cudaEventRecord(pl->join[0], pl->gather_s);
+            cudaEventRecord(pl->join[1], pl->expand_s);
+            cudaStreamWaitEvent(s, pl->join[0], 0);
+            cudaStreamWaitEvent(s, pl->join[1], 0);
+            for (int i = 0; i < Pipeline::kWave; ++i) {
+                cudaEventRecord(pl->join[2 + i], pl->wave_s[i]);
+                cudaStreamWaitEvent(s, pl->join[2 + i], 0);
+            }
+            return status;
+        }
+    }
     Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
     RNNT_TRY(launch_gather(s, p, log_probs, labels, V, blank, w.pairs, nullptr, cells), RNNT_STATUS_GATHER_FAILED);
-    RNNT_TRY(launch_wavefront(s, resolve_kind(lse_mode, false), p, w.pairs, w.alphas, w.betas, w.ll, w.bad, costs,
-                              grads == nullptr, 1, T, U),
+    RNNT_TRY(launch_wavefront(s, kind, p, w.pairs, w.alphas, w.betas, w.ll, w.bad, costs, grads == nullptr, 1, T, U),
              RNNT_STATUS_WARP_FAILED);
     if (grads) {
         ExpandSrc src = {};

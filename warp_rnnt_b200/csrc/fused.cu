@@ -456,10 +456,12 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
         static int gw_env = -1;                         // tuning knob: RNNT_B200_GATHER_WARPS in [2,16]
         if (gw_env < 0) {
             const char *e = getenv("RNNT_B200_GATHER_WARPS");
-            gw_env = e ? atoi(e) : kGatherWarps;
-            if (gw_env < 2 || gw_env > kFusedThreads / 32) gw_env = kGatherWarps;
+            gw_env = e ? atoi(e) : 0;
+            if (gw_env < 2 || gw_env > kFusedThreads / 32) gw_env = 0;
         }
-        a.gw = gw_env;
+        // fast LSE: the fill (HBM-write bound) outlasts the wavefront, so start it during the gather;
+        // exact LSE: the wavefront outlasts the fill, so let every warp gather and start it sooner
+        a.gw = gw_env ? gw_env : (kind == kFast ? kGatherWarps : kFusedThreads / 32);
     }
     const bool dense = grads != nullptr;
     const int C = plan.nw;
