@@ -165,10 +165,12 @@ struct Pipeline {
 static bool pipeline_enabled() {
     static int on = -1;
     if (on < 0) {
-        // opt-in (RNNT_B200_PIPELINE=1): measured on B200 it does not pay off yet -- cfg 4 2.96 ms
-        // pipelined vs 2.90 ms serial, cfg 5 micro-batch 2.52 vs 2.41 ms
+        // on by default (RNNT_B200_PIPELINE=0 disables).  Measured on B200, same box: cfg 5 micro-batch
+        // 2.23 ms pipelined vs 2.38 ms serial, cfg 4 2.85 vs 2.94 ms.  It only pays off with the
+        // early-retiring emit grid (launch_expand retire_early): persistent emit CTAs hold every SM
+        // until their kernel ends and the high-priority wavefront CTAs never get in (2.96 vs 2.90 ms).
         const char *e = getenv("RNNT_B200_PIPELINE");
-        on = (e && !strcmp(e, "1")) ? 1 : 0;
+        on = (e && !strcmp(e, "0")) ? 0 : 1;
     }
     return on == 1;
 }
@@ -295,7 +297,7 @@ int rnnt_b200_loss_dense(void *stream, void *workspace, size_t workspace_bytes, 
                 ExpandSrc src = {};
                 src.pairs = w.pairs + c0; src.alphas = w.alphas + c0; src.betas = w.betas + c0; src.bad = w.bad + n0;
                 src.scale = grad_scale ? grad_scale + n0 : nullptr; src.labels = lab_g; src.fastemit_lambda = fastemit_lambda;
-                if (!status && launch_expand(pl->expand_s, p, src, grads + c0 * V, cg, V, blank) != cudaSuccess)
+                if (!status && launch_expand(pl->expand_s, p, src, grads + c0 * V, cg, V, blank, true) != cudaSuccess)
                     status = RNNT_STATUS_GRADS_BLANK_FAILED;
             }
             cudaEventRecord(pl->join[0], pl->gather_s);

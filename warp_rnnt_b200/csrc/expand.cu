@@ -157,7 +157,7 @@ k_expand(Problem p, ExpandSrc src, float *__restrict__ out, int64_t cells, int V
 }
 
 cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src, float *out, int64_t cells,
-                          int V, int blank) {
+                          int V, int blank, bool retire_early) {
     if (cells <= 0) return cudaSuccess;
     int rows = (int)(65536 / ((int64_t)V * 4));
     rows = max(1, min(rows, kExpandMaxRows));
@@ -165,7 +165,10 @@ cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src
     int sms = 148;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = (int)(nchunks < (int64_t)sms * 8 ? nchunks : (int64_t)sms * 8);
+    // persistent CTAs by default; retire_early = one CTA per few chunks, so that SM resources keep freeing
+    // up for the high-priority wavefront CTAs of the pipelined path
+    const int64_t cap = retire_early ? (int64_t)sms * 64 : (int64_t)sms * 8;
+    const int grid = (int)(nchunks < cap ? nchunks : cap);
     const FastDiv divV((uint32_t)V), divU((uint32_t)max(p.U, 1)), divTU((uint32_t)max(p.T * p.U, 1));
     const int vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) ? 1 : 0;
     const int mode = p.compact ? 2 : (src.pg ? 1 : 0);

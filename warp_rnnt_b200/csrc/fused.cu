@@ -373,16 +373,31 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
             const int r0 = t0, r1 = min(t1, Tn);
             const int cells = (r1 - r0) * Un;
             const float inv = 1.0f / (float)Un;
-#pragma unroll 4
-            for (int c = tid; c < cells; c += kFusedThreads) {
-                int tt = (int)(((float)c + 0.5f) * inv);
-                int u = c - tt * Un;
-                if (u < 0) { --tt; u += Un; } else if (u >= Un) { ++tt; u -= Un; }
-                const int t = r0 + tt;
-                const float2 gq = cell_grad(t, u);
-                float *row = A.grads + (slab + (int64_t)t * U + u) * V;
-                if (!(t == T1 && u < U1)) row[A.blank] = gq.x;
-                if (u < U1) row[s_lab[u]] = gq.y;       // after the blank: a label equal to blank wins (core.cu:383-390)
+            // four cells per thread and pass: all shared-memory reads and both expf chains of the four
+            // cells first (independent, so they overlap), then the eight scattered stores
+            constexpr int G = 4;
+            for (int cb = tid; cb < cells; cb += kFusedThreads * G) {
+                float2 gq[G];
+                int tq[G], uq[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const int c = cb + g * kFusedThreads;
+                    int tt = (int)(((float)c + 0.5f) * inv);
+                    int u = c - tt * Un;
+                    if (u < 0) { --tt; u += Un; } else if (u >= Un) { ++tt; u -= Un; }
+                    const bool in = c < cells;
+                    tq[g] = in ? r0 + tt : -1;
+                    uq[g] = in ? u : 0;
+                    gq[g] = in ? cell_grad(r0 + tt, u) : make_float2(0.0f, 0.0f);
+                }
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const int t = tq[g], u = uq[g];
+                    if (t < 0) continue;
+                    float *row = A.grads + (slab + (int64_t)t * U + u) * V;
+                    if (!(t == T1 && u < U1)) row[A.blank] = gq[g].x;
+                    if (u < U1) row[s_lab[u]] = gq[g].y;   // after the blank: a label equal to blank wins (core.cu:383-390)
+                }
             }
         }
     } else if (A.pair_grads) {
@@ -414,7 +429,9 @@ bool fused_plan(int N, int T, int U, FusedPlan *plan) {
     if (smem > 220 * 1024) return false;
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int slices = sms / N;
+    // CTAs per lattice: fill every SM (two CTAs per SM when two staged lattices fit in its shared memory)
+    const int per_sm = (smem <= 110 * 1024) ? 2 : 1;
+    int slices = (per_sm * sms) / N;
     slices = max(1, min(slices, T));
     plan->W = Wd; plan->ring = nd; plan->nw = C; plan->slices = slices; plan->smem = smem;
     return true;

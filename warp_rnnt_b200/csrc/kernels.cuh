@@ -34,7 +34,7 @@ struct ExpandSrc {
     int label_adds;          // 1: label == blank accumulates (torch scatter_add semantics of gather=True)
 };
 cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src, float *out, int64_t cells,
-                          int V, int blank);
+                          int V, int blank, bool retire_early = false);
 
 // fused.cu -- single-kernel path for lattices that fit shared memory
 struct FusedPlan { int W, ring, nw, slices; size_t smem; };
