@@ -237,6 +237,7 @@ void rnnt_b200_set_lse_mode(int mode) {
 int rnnt_b200_get_lse_mode(void) { return default_lse_mode(); }
 
 uint64_t rnnt_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void rnnt_b200_debug_fused_trace(void *buf) { rnnt::set_fused_trace(static_cast<long long *>(buf)); }
 
 size_t rnnt_b200_workspace_bytes(int64_t cells, int N) { return carve(nullptr, cells, N).bytes; }
 

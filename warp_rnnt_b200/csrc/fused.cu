@@ -2,9 +2,12 @@
 // ((T+U)*U <~ 9k cells: BASELINE configs 1-3).  One launch does everything the reference spreads
 // over zeros_like + 4 kernels (+ python gather / mul_):
 //
-//   phase 0  gather      all warps stage the lattice's blank/label log-probs into shared memory in
+//   phase 0  gather      14 warps stage the lattice's blank/label log-probs into shared memory in
 //                        DIAGONAL-MAJOR, target-indexed form (replaces the python-level gather,
-//                        __init__.py:118-128, and the strided loads inside kernel_warp, core.cu:115-120)
+//                        __init__.py:118-128, and the strided loads inside kernel_warp, core.cu:115-120).
+//                        Rows are staged from both ends towards the middle in 128-cell chunks, each
+//                        published with a release flag, so the two wavefronts START WHILE THE GATHER IS
+//                        STILL RUNNING and chase it (alpha needs the top rows first, beta the bottom rows)
 //   phase 1  wavefront   ONE warp runs alpha and one runs beta: lane l owns C adjacent lattice columns,
 //                        every anti-diagonal is one step = one __shfl_up + C independent LSE chains,
 //                        operands and results move as C-wide vector LDS/STS (conflict-free, because a
@@ -29,7 +32,6 @@
 namespace rnnt {
 
 constexpr int kFusedThreads = 512;
-constexpr int kGatherWarps = 12;    // MODE 0: warps that stage log-probs; the other 4 start the zero-fill at once
 constexpr float kBigF = -1.0e30f;   // finite stand-in for -inf (see wavefront.cu)
 
 // L2 residency control (B200: 126 MB L2).  The dense gradient slab is zero-filled while the
@@ -55,6 +57,82 @@ __device__ __forceinline__ float2 ldg_hint2(const float2 *ptr, uint64_t pol) {
 __device__ __forceinline__ void stg_zero256_evict_last(float *ptr) {
     asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(ptr), "r"(0) : "memory");
 }
+
+// Zero-fill through the TMA engine: bulk shared->global copies of a zeroed shared-memory buffer,
+// evict_last in L2.  One thread issues 8 KB per instruction, so the fill costs the SM no LSU / MIO
+// queue slots -- with STG fills the queue stays full of back-pressured stores and the wavefront
+// warps' LDS/STS wait behind them (measured: exact-LSE step 330 ns with STG fill running, 160 ns alone).
+constexpr int kZeroBytes = 8192;
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(gdst), "r"(ssrc), "r"(bytes), "l"(pol) : "memory");
+}
+
+// TMA row gather: one bulk global->shared copy per lattice row (U*V contiguous floats), completion
+// on an mbarrier.  The whole row is read -- HBM has to deliver it anyway (64-byte atoms: the two
+// 4-byte picks per 112-byte cell touch nearly every atom) -- but as full lines by the copy engine
+// instead of as ~60 L1 line look-ups per 32 cells, which is what bounded the LDG gather.
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_load(uint32_t sdst, const void *gsrc, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+constexpr int kMaxRowBufs = 14;                               // one per gather warp
+
+// chunk flags: gather warps publish, wavefront warps consume (same CTA, shared memory)
+__device__ __forceinline__ void flag_release(int *f) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(f)), "r"(1) : "memory");
+}
+__device__ __forceinline__ int flag_acquire(const int *f) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(f)) : "memory");
+    return v;
+}
+constexpr int kChunkLog = 7, kChunkCells = 1 << kChunkLog;   // gather granule: 4 cells per lane
+constexpr int kMaxChunks = 96;                                 // >= ceil(max staged cells / kChunkCells)
+
+// Consumer side of the gather.  Order-row k: even k = top row k/2, odd k = bottom row Tn-1-(k-1)/2.
+// A wavefront that is about to read lattice rows within m of its starting edge needs order-rows
+// <= 2m+1 staged.
+//   chunked LDG gather : chunk q holds order-space cells [128q, 128q+128); flag[q] set when staged
+//   TMA row gather     : gather warp g stages order-rows g, g+gwn, ...; flag[g] counts its finished rows
+struct GatherWait {
+    const int *flag;
+    int Un, Tn, lane, gwn;  // gwn > 0: TMA row gather with gwn warps
+    int ready;              // chunks [0, ready) / order-rows [0, ready) are known complete
+    __device__ __forceinline__ void rows(int m) {
+        const int k = min(2 * m + 1, Tn - 1);
+        if (gwn > 0) {
+            while (ready <= k) {
+                int first_open = 0x7fffffff;          // this gather warp's first unfinished order-row
+                if (lane < gwn) first_open = flag_acquire(flag + lane) * gwn + lane;
+                ready = __reduce_min_sync(0xffffffffu, first_open);
+            }
+        } else {
+            const int q = ((k + 1) * Un - 1) >> kChunkLog;
+            while (ready <= q) {
+                while (flag_acquire(flag + ready) == 0) {}
+                ++ready;
+            }
+        }
+    }
+};
 
 // C-wide shared-memory vector load / store (C in {1,2,4,8}); asm volatile keeps program order so
 // the operand prefetch stays where it is written.
@@ -96,9 +174,13 @@ struct FusedArgs {
     int N, T, U, V, blank;
     float lam;
     int pairs_in, guard, slices;
+    int zoff;               // byte offset of the zero buffer in dynamic shared memory
+    int nbuf, row_off, row_stride;   // TMA row gather: buffers (0 = LDG gather), their byte offset and stride
     int Wd;                 // staged row stride (floats) = C * ceil(U / C), even
     int nd;                 // staged rows (diagonals) allocated = T + Wd + 16
-    int gw;                 // MODE 0: warps that gather; the rest start the zero-fill immediately
+    int gw;                 // warps that gather (of the 14 non-wavefront warps); MODE 0: the rest start the zero-fill at once
+    int tma_fill;           // MODE 0: zero-fill with bulk shared->global copies (else 256-bit STG)
+    long long *trace;       // optional per-CTA phase stamps (clock64), 8 per CTA; null = off
 };
 
 // One direction of one lattice, one warp.  Diagonal-major, target-indexed operands:
@@ -113,25 +195,47 @@ struct FusedArgs {
 // (column edge): inside a lane that is a register, across lanes one __shfl_up of the lane's last column.
 template <int KIND, int C>
 __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t out, int Wd, int ndiag, int lane,
-                                           int first_col, const float *pre, int pre_rows) {
+                                           int first_col, const float *pre, int pre_rows, GatherWait gw,
+                                           long long *trace) {
     constexpr int P = (C <= 2) ? 4 : 2;                       // diagonals of operand prefetch
     float val[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) val[c] = (C * lane + c == first_col) ? 0.0f : kBigF;
-    const uint32_t stride = 4u * (uint32_t)Wd;
+    // The loop below is one long dependent chain (shuffle -> add -> LSE -> shuffle ...) on an in-order
+    // pipeline: anything that stalls ISSUE stalls the chain.  So the row stride lives in a register the
+    // compiler cannot rematerialise from the constant bank (a per-step LDC + dependent IMAD cost ~40
+    // cycles), the exact-mode column override is a prefetched select instead of a divergent branch
+    // around a shared-memory load, and the gather hand-shake is checked once per P steps.
+    uint32_t stride = 4u * (uint32_t)Wd;
+    asm volatile("" : "+r"(stride));
     const uint32_t off = 4u * (uint32_t)(C * lane);
     uint32_t a_wb = wb + off, a_wl = wl + off, a_out = out + off;
-    float b[P][C], l[P][C];
+    // exact mode: the first real column is taken from the reference-order prefix scan (core.cu:92-110)
+    const int l0 = first_col / C, c0 = first_col - l0 * C;
+    bool own[C];                                              // this register holds the first real column
+#pragma unroll
+    for (int c = 0; c < C; ++c) own[c] = (KIND != kFast) && lane == l0 && c == c0;
+    const uint32_t a_pre = (uint32_t)__cvta_generic_to_shared(pre);
+    auto pre_at = [&](int d) -> float {                      // scan value for diagonal d (clamped; unused when out of range)
+        const int i = min(max(d - first_col, 0), pre_rows - 1);
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a_pre + 4u * (uint32_t)i) : "memory");
+        return v;
+    };
+    const bool in_row = C * lane < Wd;                         // (results are written in place over operands, see k_fused)
+    float b[P][C], l[P][C], pv[P];
+    gw.rows(P - 1);                                           // diagonals 0..P-1 touch rows <= P-1
 #pragma unroll
     for (int k = 0; k < P; ++k) {
         lds_vec<C>(a_wb, b[k]);
         lds_vec<C>(a_wl, l[k]);
+        if (KIND != kFast) pv[k] = pre_at(k);
         a_wb += stride;
         a_wl += stride;
     }
-    // exact mode: the first real column is taken from the reference-order prefix scan (core.cu:92-110)
-    const int l0 = first_col / C, c0 = first_col - l0 * C;
     for (int d0 = 0; d0 < ndiag; d0 += P) {
+        if (trace && lane == 0 && (d0 & 31) == 0 && d0 < 256) trace[8 + (d0 >> 5)] = clock64();   // diagnostics only
+        gw.rows(d0 + 2 * P - 1);                               // the gather has staged every row this iteration prefetches
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             const float left = __shfl_up_sync(0xffffffffu, val[C - 1], 1);   // lane 0 gets its own value: wl = kBig there
@@ -141,19 +245,17 @@ __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t ou
             for (int c = 1; c < C; ++c) nv[c] = lse<KIND>(val[c] + b[k][c], val[c - 1] + l[k][c]);
             if (KIND != kFast) {
                 const int i = d0 + k - first_col;              // row of the first real column on this diagonal
-                if (lane == l0 && i >= 1 && i < pre_rows) {
-                    const float p = pre[i];
+                const bool in = (i >= 1) && (i < pre_rows);
 #pragma unroll
-                    for (int c = 0; c < C; ++c)
-                        if (c == c0) nv[c] = p;
-                }
+                for (int c = 0; c < C; ++c) nv[c] = (own[c] && in) ? pv[k] : nv[c];
             }
 #pragma unroll
             for (int c = 0; c < C; ++c) val[c] = nv[c];
-            sts_vec<C>(a_out, val);
+            if (in_row) sts_vec<C>(a_out, val);              // lanes past the staged row must not spill into the next one
             a_out += stride;
             lds_vec<C>(a_wb, b[k]);                            // operands P diagonals ahead (rows past ndiag are allocated)
             lds_vec<C>(a_wl, l[k]);
+            if (KIND != kFast) pv[k] = pre_at(d0 + k + P);
             a_wb += stride;
             a_wl += stride;
         }
@@ -171,19 +273,30 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     const bool ok = (Tn >= 1 && Tn <= T && Un >= 1 && Un <= U);
     const int T1 = Tn - 1, U1 = Un - 1;
 
-    // ---- shared memory carve-up: six diagonal-major arrays [nd][Wd], prefix-scan columns, labels
+    // ---- shared memory carve-up: five diagonal-major arrays [nd][Wd], prefix-scan columns, labels
     const size_t plane = (size_t)A.nd * Wd;
     float *WBa = reinterpret_cast<float *>(smem_raw);   // alpha: blank edge into (t,u)   at [t+u][u]
     float *WLa = WBa + plane;                           // alpha: label edge into (t,u)   at [t+u][u]
     float *WBb = WLa + plane;                           // beta : blank edge out of (t,u) at [d'][j'], j' = Wd-1-u, d' = (T1-t)+j'
     float *WLb = WBb + plane;                           // beta : label edge out of (t,u) at [d'][j']
-    float *AL = WLb + plane;                            // alpha[t,u] at [t+u][u]
-    float *BE = AL + plane;                             // beta[t,u]  at [d'][j']
+    float *AL = WLa;                                    // alpha[t,u] at [t+u][u]: IN PLACE over its label edges -- the
+                                                        // wavefront has read slot [d][j] P steps before it writes it;
+                                                        // phase 2 takes the log-probs from the beta-side copies
+    float *BE = WLb + plane;                            // beta[t,u]  at [d'][j']
     float *preA = BE + plane;                           // [T] exact-mode column scans
     float *preB = preA + T;
     int *s_lab = reinterpret_cast<int *>(preB + T);     // [U]
+    // zero buffer for the bulk fill: the last kZeroBytes of the dynamic allocation (128-byte aligned)
+    float *zbuf = reinterpret_cast<float *>(smem_raw + A.zoff);
     __shared__ int s_next;                              // fill work counter
     __shared__ int s_bad;
+    __shared__ int s_flag[kMaxChunks];                  // gather chunk q staged / rows finished by gather warp g
+    __shared__ __align__(8) unsigned long long s_bar[kMaxRowBufs];   // TMA row gather: one mbarrier per buffer
+    long long *trace = A.trace ? A.trace + 16 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+    auto stamp = [&](int slot) {                        // latest arrival per phase
+        if (trace && lane == 0) atomicMax(reinterpret_cast<unsigned long long *>(trace) + slot, (unsigned long long)clock64());
+    };
+    stamp(0);
     auto idxA = [&](int t, int u) { return (t + u) * Wd + u; };
     auto idxB = [&](int t, int u) { const int jp = Wd - 1 - u; return (T1 - t + jp) * Wd + jp; };
 
@@ -193,6 +306,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
 
     // ---- phase 0: sentinels, labels, gather
     if (tid == 0) { s_next = 0; s_bad = ok ? 0 : 1; }
+    if (tid < kMaxChunks) s_flag[tid] = 0;
+    if (tid < A.nbuf) mbar_init((uint32_t)__cvta_generic_to_shared(&s_bar[tid]), 1);
+    if (A.nbuf > 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (MODE == 0 && A.tma_fill) {
+        for (int k = tid; k < kZeroBytes / 4; k += kFusedThreads) zbuf[k] = 0.0f;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros -> async-proxy reads
+    }
     if (ok) {
         const int used = (Tn + Wd + 8) * Wd;            // diagonals any sweep or its prefetch can touch
         const int lim = min(used, (int)plane);
@@ -204,33 +324,71 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
             for (int u = tid; u < U1; u += kFusedThreads) s_lab[u] = A.labels[(int64_t)n * (U - 1) + u];
     }
     __syncthreads();
-    // MODE 0: warps [0,GW) gather, then warps 0/1 sweep and the rest of them join the zero-fill that
-    // warps [GW,32) started right after the barrier above: HBM reads (gather) and writes (fill) overlap.
-    // The fill is HBM-write bound (~20 us for cfg 2's 86 MB) and the gather HBM-read bound (~14 us);
-    // serialising them costs their sum, overlapping them costs ~the larger.
-    const int GW = (MODE == 0) ? A.gw : kFusedThreads / 32;
-    const int gthreads = GW * 32;
+    stamp(1);
     // Roles go by a rotated warp index: the two wavefront warps are the HIGHEST-numbered hardware
     // warps (14 and 15, on different sub-partitions).  The SM's issue arbiter favours higher warp
     // ids, so the latency-critical recurrence is never starved by the fill / gather warps sharing its
     // scheduler (with the sweep on warps 0/1 the exact flavour measured anywhere from 65 to 250 us).
+    //   logical warp 0 / 1      alpha / beta wavefront, chasing the gather chunk by chunk
+    //   logical warps [2,2+GW)  gather, then (MODE 0) zero-fill
+    //   the rest (MODE 0)       zero-fill from the start: HBM reads (gather) and writes (fill) overlap
     const int lw = (warp + 2) & (kFusedThreads / 32 - 1);
-    const int ltid = lw * 32 + lane;
-    if (ok && lw < GW) {
-        const int cells = Tn * Un;
+    const int GW = A.gw;
+    const int cells_n = ok ? Tn * Un : 0;
+    const int nchunks = (cells_n + kChunkCells - 1) >> kChunkLog;
+    if (A.nbuf > 0) {
+        // TMA row gather: gather warp g owns row buffer g and stages order-rows g, g+nbuf, ...
+        if (ok && lw >= 2 && lw < 2 + A.nbuf) {
+            const int g = lw - 2;
+            const float *buf = reinterpret_cast<const float *>(smem_raw + A.row_off + (size_t)g * A.row_stride);
+            const uint32_t buf_s = (uint32_t)__cvta_generic_to_shared(buf);
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[g]);
+            const uint64_t pol_first = policy_evict_first();
+            const uint32_t bytes = ((uint32_t)(Un * V) * 4u + 15u) & ~15u;   // <= U*V*4, which is a multiple of 16
+            uint32_t phase = 0;
+            int done = 0;
+            for (int k = g; k < Tn; k += A.nbuf) {
+                const int t = (k & 1) ? T1 - (k >> 1) : (k >> 1);   // rows alternate: top, bottom, top, ...
+                if (lane == 0) {
+                    mbar_expect_tx(bar, bytes);
+                    bulk_load(buf_s, A.lp + (slab + (int64_t)t * U) * V, bytes, bar, pol_first);
+                }
+                while (!mbar_try_wait(bar, phase)) {}
+                phase ^= 1u;
+                for (int u = lane; u < Un; u += 32) {
+                    const float vb = buf[u * V + A.blank];
+                    const float vl = (u < U1) ? buf[u * V + s_lab[u]] : kBigF;
+                    const int ib = idxB(t, u);
+                    WBb[ib] = vb;
+                    WLb[ib] = vl;                       // kBig on the last column: beta's first column has no column edge
+                    if (t < T1) WBa[idxA(t + 1, u)] = vb;
+                    if (u < U1) WLa[idxA(t, u + 1)] = vl;
+                }
+                __syncwarp();                           // every lane is done with the buffer and has staged its cells
+                if (lane == 0) {
+                    ++done;
+                    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_flag[g])), "r"(done) : "memory");
+                }
+            }
+            stamp(2);
+        }
+        // the zero-fill starts when the whole gather is done (HBM serves the critical reads first)
+        if (MODE == 0 && lw >= 2) asm volatile("bar.sync 1, %0;" ::"r"(kFusedThreads - 64) : "memory");
+    } else if (ok && lw >= 2 && lw < 2 + GW) {
         const float inv = 1.0f / (float)Un;
         const uint64_t pol_first = policy_evict_first();
-        constexpr int G = 4;                            // cells per thread per pass: all loads first
-        for (int cb = ltid; cb < cells; cb += gthreads * G) {
+        constexpr int G = kChunkCells / 32;             // cells per lane per chunk: all loads first
+        for (int q = lw - 2; q < nchunks; q += GW) {
             float vb[G], vl[G];
             int tt[G], uu[G];
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                const int c = cb + g * gthreads;
-                const bool in = c < cells;
-                int t = (int)(((float)c + 0.5f) * inv);
-                int u = c - t * Un;
-                if (u < 0) { --t; u += Un; } else if (u >= Un) { ++t; u -= Un; }
+                const int c = (q << kChunkLog) + g * 32 + lane;   // cell index in order-space
+                const bool in = c < cells_n;
+                int k = (int)(((float)c + 0.5f) * inv);            // order-row
+                int u = c - k * Un;
+                if (u < 0) { --k; u += Un; } else if (u >= Un) { ++k; u -= Un; }
+                int t = (k & 1) ? T1 - (k >> 1) : (k >> 1);        // rows alternate: top, bottom, top, ...
                 if (!in) { t = 0; u = 0; }
                 tt[g] = in ? t : -1;
                 uu[g] = u;
@@ -257,27 +415,42 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
                     if (u < U1) WLa[idxA(t, u + 1)] = vl[g];
                 }
             }
+            __syncwarp();
+            if (lane == 0) flag_release(&s_flag[q]);
         }
+        stamp(2);
     }
-    if (GW == kFusedThreads / 32) __syncthreads();
-    else if (lw < GW) asm volatile("bar.sync 1, %0;" ::"r"(gthreads) : "memory");   // gather warps only
 
     // ---- phase 1: logical warp 0 = alpha, 1 = beta (then both help filling); other warps zero-fill
     if (ok && lw < 2) {
         const bool beta = (lw == 1);
         const int first_col = beta ? (Wd - Un) : 0;
         const int ndiag = beta ? (Tn + Wd - 1) : (Tn + Un - 1);
-        const float *wbp = beta ? WBb : WBa;
         float *pre = beta ? preB : preA;
         if (KIND != kFast) {
             // column 0 in the reference's summation order: 32-wide Kogge-Stone scan per tile + the tile's
-            // base (core.cu:92-110 / :197-215), so that exact mode is bit-identical
-            float base = beta ? wbp[first_col * Wd + first_col] : 0.0f;
-            if (lane == 0) pre[0] = base;
+            // base (core.cu:92-110 / :197-215), so that exact mode is bit-identical.  The column's blank
+            // edges are fetched straight from HBM by this warp (the gather is still in flight):
+            // pre[0] = base, pre[i] = edge into row i of the first column.
+            for (int i0 = lane; i0 <= T1; i0 += 256) {  // eight loads in flight per lane
+                float v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = min(i0 + 32 * k, T1);
+                    const int64_t cell = slab + (beta ? ((int64_t)(T1 - i) * U + U1) : ((int64_t)max(i - 1, 0) * U));
+                    v[k] = A.pairs_in ? __ldg(reinterpret_cast<const float2 *>(A.lp) + cell).x : __ldg(A.lp + cell * V + A.blank);
+                    if (!beta && i == 0) v[k] = 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (i0 + 32 * k <= T1) pre[i0 + 32 * k] = v[k];
+            }
+            __syncwarp();
+            float base = pre[0];
             for (int p0 = 0; p0 < T1; p0 += 32) {
                 const int i = p0 + lane + 1;
                 float bsum = 0.0f;
-                if (i <= T1) bsum = wbp[(i + first_col) * Wd + first_col];   // blank edge into row i of the first column
+                if (i <= T1) bsum = pre[i];             // blank edge into row i of the first column
 #pragma unroll
                 for (int k = 1; k < 32; k <<= 1) {
                     const float a = __shfl_up_sync(0xffffffffu, bsum, k);
@@ -289,10 +462,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
             }
             __syncwarp();
         }
-        const uint32_t wb_a = (uint32_t)__cvta_generic_to_shared(wbp);
+        const uint32_t wb_a = (uint32_t)__cvta_generic_to_shared(beta ? WBb : WBa);
         const uint32_t wl_a = (uint32_t)__cvta_generic_to_shared(beta ? WLb : WLa);
         const uint32_t out_a = (uint32_t)__cvta_generic_to_shared(beta ? BE : AL);
-        sweep_diag<KIND, C>(wb_a, wl_a, out_a, Wd, ndiag, lane, first_col, pre, Tn);
+        GatherWait gwait;
+        gwait.flag = s_flag; gwait.Un = Un; gwait.Tn = Tn; gwait.ready = 0; gwait.lane = lane; gwait.gwn = A.nbuf;
+        stamp(3);
+        sweep_diag<KIND, C>(wb_a, wl_a, out_a, Wd, ndiag, lane, first_col, pre, Tn, gwait, beta ? nullptr : trace);
+        stamp(beta ? 5 : 4);
     }
     if (MODE == 0) {
         // zero-fill rows [t0,t1) of this lattice's slab: floats [f0,f1); 32 KB chunks handed out by
@@ -303,21 +480,41 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         const int64_t a0 = vec ? min(f1, (f0 + 7) & ~(int64_t)7) : f1;
         const int64_t a1 = vec ? max(a0, f1 & ~(int64_t)7) : f1;
         constexpr int kChunk = 8192;                    // floats per chunk
-        const int64_t nchunks = (a1 - a0 + kChunk - 1) / kChunk;
-        for (;;) {
-            int c = 0;
-            if (lane == 0) c = atomicAdd(&s_next, 1);
-            c = __shfl_sync(0xffffffffu, c, 0);
-            if (c >= nchunks) break;
-            const int64_t b = a0 + (int64_t)c * kChunk;
-            const int64_t e = min(a1, b + kChunk);
+        const int64_t nfill = (a1 - a0 + kChunk - 1) / kChunk;
+        if (A.tma_fill) {
+            if (lane == 0) {
+                const uint64_t pol = policy_evict_last();
+                const uint32_t zs = (uint32_t)__cvta_generic_to_shared(zbuf);
+                for (;;) {
+                    const int c = atomicAdd(&s_next, 1);
+                    if (c >= nfill) break;
+                    const int64_t b = a0 + (int64_t)c * kChunk;
+                    const int64_t e = min(a1, b + kChunk);
+                    for (int64_t f = b; f < e; f += kZeroBytes / 4)
+                        bulk_store(g + f, zs, (uint32_t)(min(e - f, (int64_t)(kZeroBytes / 4)) * 4), pol);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the zeros have landed ...
+                asm volatile("fence.proxy.async;" ::: "memory");            // ... before anyone patches them
+            }
+            __syncwarp();
+        } else {
+            for (;;) {
+                int c = 0;
+                if (lane == 0) c = atomicAdd(&s_next, 1);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= nfill) break;
+                const int64_t b = a0 + (int64_t)c * kChunk;
+                const int64_t e = min(a1, b + kChunk);
 #pragma unroll 4
-            for (int64_t f = b + 8 * lane; f < e; f += 256) stg_zero256_evict_last(g + f);
+                for (int64_t f = b + 8 * lane; f < e; f += 256) stg_zero256_evict_last(g + f);
+            }
         }
         if (lw == kFusedThreads / 32 - 1) {             // unaligned head / tail (<= 7 floats each, or all if !vec)
             for (int64_t f = f0 + lane; f < a0; f += 32) g[f] = 0.0f;
             for (int64_t f = a1 + lane; f < f1; f += 32) g[f] = 0.0f;
         }
+        stamp(6);
     }
     __syncthreads();
 
@@ -411,11 +608,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
             A.pair_grads[slab + (int64_t)t * U + u] = gq;
         }
     }
+    stamp(7);
 }
 
 // ---- host side -------------------------------------------------------------------------------
+constexpr int kFusedMaxDynSmem = 225 * 1024;           // 227 KB per CTA minus the kernel's static shared memory
+static long long *g_fused_trace = nullptr;             // diagnostics: see rnnt_b200_debug_fused_trace
+void set_fused_trace(long long *buf) { g_fused_trace = buf; }
+
+static size_t fused_zero_offset(int T, int U, int Wd, int nd) {
+    const size_t used = sizeof(float) * ((size_t)5 * nd * Wd + (size_t)2 * T) + sizeof(int) * (size_t)U;
+    return (used + 127) / 128 * 128;
+}
 static size_t fused_smem_bytes(int T, int U, int Wd, int nd) {
-    return sizeof(float) * ((size_t)6 * nd * Wd + (size_t)2 * T) + sizeof(int) * (size_t)U + 64;
+    return fused_zero_offset(T, U, Wd, nd) + kZeroBytes;
 }
 
 // Can the fused kernel take this shape?  Fills `plan` with the derived launch parameters.
@@ -427,6 +633,7 @@ bool fused_plan(int N, int T, int U, FusedPlan *plan) {
     const int nd = T + Wd + 16;                         // diagonals + prefetch overshoot
     const size_t smem = fused_smem_bytes(T, U, Wd, nd);
     if (smem > 220 * 1024) return false;
+    if (((int64_t)T * U + kChunkCells - 1) / kChunkCells > kMaxChunks) return false;
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // CTAs per lattice: fill every SM (two CTAs per SM when two staged lattices fit in its shared memory)
@@ -441,7 +648,7 @@ template <int KIND, int MODE, int C>
 static cudaError_t launch_fused_kmc(cudaStream_t s, const FusedArgs &a, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_fused<KIND, MODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_fused<KIND, MODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedMaxDynSmem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -474,18 +681,47 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
         if (gw_env < 0) {
             const char *e = getenv("RNNT_B200_GATHER_WARPS");
             gw_env = e ? atoi(e) : 0;
-            if (gw_env < 2 || gw_env > kFusedThreads / 32) gw_env = 0;
+            if (gw_env < 1 || gw_env > kFusedThreads / 32 - 2) gw_env = 0;
         }
         // fast LSE: the fill (HBM-write bound) outlasts the wavefront, so start it during the gather;
-        // exact LSE: the wavefront outlasts the fill, so let every warp gather and start it sooner
-        a.gw = gw_env ? gw_env : (kind == kFast ? kGatherWarps : kFusedThreads / 32);
+        // exact LSE: the wavefront outlasts the fill, so let every free warp gather and feed it sooner
+        // (measured with the TMA fill: starting the fill only when the gather is done is best in both modes)
+        a.gw = gw_env ? gw_env : kFusedThreads / 32 - 2;
+        if (!grads) a.gw = kFusedThreads / 32 - 2;      // nothing to fill: everyone gathers
     }
+    a.zoff = (int)(plan.smem - kZeroBytes);
+    // TMA row gather when a lattice row (U*V floats) is a 16-byte multiple at a 16-byte aligned address and
+    // at least four row buffers fit behind the planes (RNNT_B200_GATHER=ldg forces the LDG gather)
+    size_t smem = plan.smem;
+    a.nbuf = 0; a.row_off = 0; a.row_stride = 0;
+    {
+        static int want_tma = -1;
+        if (want_tma < 0) { const char *e = getenv("RNNT_B200_GATHER"); want_tma = (e && e[0] == 'l') ? 0 : 1; }
+        const size_t row = (size_t)U * V * sizeof(float);
+        const size_t stride = (row + 127) / 128 * 128;
+        // keep two CTAs per SM where the plan counted on them
+        const size_t cap = (plan.smem <= 110 * 1024) ? (size_t)113 * 1024 : (size_t)kFusedMaxDynSmem;
+        if (want_tma && !pairs_in && (row % 16) == 0 && (reinterpret_cast<uintptr_t>(lp) % 16) == 0 && row <= 32 * 1024 &&
+            plan.smem + 4 * stride <= cap) {
+            const int nb = (int)((cap - plan.smem) / stride);
+            a.nbuf = nb < kMaxRowBufs ? nb : kMaxRowBufs;
+            a.row_off = (int)plan.smem;
+            a.row_stride = (int)stride;
+            smem = plan.smem + (size_t)a.nbuf * stride;
+        }
+    }
+    {
+        static int tma = -1;                            // RNNT_B200_FILL=stg selects the 256-bit store fill
+        if (tma < 0) { const char *e = getenv("RNNT_B200_FILL"); tma = (e && e[0] == 's') ? 0 : 1; }
+        a.tma_fill = tma;
+    }
+    a.trace = g_fused_trace;
     const bool dense = grads != nullptr;
     const int C = plan.nw;
     if (kind == kFast)
-        return dense ? launch_fused_km<kFast, 0>(s, a, plan.smem, C) : launch_fused_km<kFast, 1>(s, a, plan.smem, C);
+        return dense ? launch_fused_km<kFast, 0>(s, a, smem, C) : launch_fused_km<kFast, 1>(s, a, smem, C);
     // dense-layout exact flavour (the compact layout never takes the fused path)
-    return dense ? launch_fused_km<kExactDense, 0>(s, a, plan.smem, C) : launch_fused_km<kExactDense, 1>(s, a, plan.smem, C);
+    return dense ? launch_fused_km<kExactDense, 0>(s, a, smem, C) : launch_fused_km<kExactDense, 1>(s, a, smem, C);
 }
 
 }  // namespace rnnt

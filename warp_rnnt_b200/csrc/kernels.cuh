@@ -39,6 +39,7 @@ cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src
 // fused.cu -- single-kernel path for lattices that fit shared memory
 struct FusedPlan { int W, ring, nw, slices; size_t smem; };
 bool fused_plan(int N, int T, int U, FusedPlan *plan);
+void set_fused_trace(long long *buf);   // diagnostics: per-CTA phase stamps of k_fused (8 x clock64 per CTA)
 cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const float *lp, const int *labels,
                          const int *xn, const int *yn, float *costs, float *grads, float2 *pair_grads,
                          const float *scale, int N, int T, int U, int V, int blank, float lam, int pairs_in,
