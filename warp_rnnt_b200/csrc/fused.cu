@@ -315,10 +315,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     }
     if (ok) {
         const int used = (Tn + Wd + 8) * Wd;            // diagonals any sweep or its prefetch can touch
-        const int lim = min(used, (int)plane);
-        for (int k = tid; k < lim; k += kFusedThreads) {
-            WBa[k] = 0.0f; WBb[k] = 0.0f;
-            WLa[k] = kBigF; WLb[k] = kBigF;
+        const int lim4 = min((used + 3) >> 2, (int)(plane >> 2));   // planes are whole float4s (nd, Wd even)
+        const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), b4 = make_float4(kBigF, kBigF, kBigF, kBigF);
+        for (int k = tid; k < lim4; k += kFusedThreads) {
+            reinterpret_cast<float4 *>(WBa)[k] = z4; reinterpret_cast<float4 *>(WBb)[k] = z4;
+            reinterpret_cast<float4 *>(WLa)[k] = b4; reinterpret_cast<float4 *>(WLb)[k] = b4;
         }
         if (!A.pairs_in)
             for (int u = tid; u < U1; u += kFusedThreads) s_lab[u] = A.labels[(int64_t)n * (U - 1) + u];
@@ -571,29 +572,45 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
             const int cells = (r1 - r0) * Un;
             const float inv = 1.0f / (float)Un;
             // four cells per thread and pass: all shared-memory reads and both expf chains of the four
-            // cells first (independent, so they overlap), then the eight scattered stores
+            // cells first (independent, so they overlap), then the scattered stores.  A store instruction
+            // costs the LSU one pass per 128-byte line it touches, and a cell is 4*V bytes wide, so the
+            // stores are issued with lanes (2k, 2k+1) = (blank, label) of ONE cell: 16 adjacent cells per
+            // instruction (~half the lines of 32 blanks followed by 32 labels).
             constexpr int G = 4;
-            for (int cb = tid; cb < cells; cb += kFusedThreads * G) {
+            for (int base = warp * 32; base < cells; base += kFusedThreads * G) {   // warp-uniform trip count
                 float2 gq[G];
-                int tq[G], uq[G];
+                int key[G], olf[G];
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const int c = cb + g * kFusedThreads;
+                    const int c = base + g * kFusedThreads + lane;
                     int tt = (int)(((float)c + 0.5f) * inv);
                     int u = c - tt * Un;
                     if (u < 0) { --tt; u += Un; } else if (u >= Un) { ++tt; u -= Un; }
                     const bool in = c < cells;
-                    tq[g] = in ? r0 + tt : -1;
-                    uq[g] = in ? u : 0;
-                    gq[g] = in ? cell_grad(r0 + tt, u) : make_float2(0.0f, 0.0f);
+                    const int t = r0 + tt;
+                    gq[g] = in ? cell_grad(t, in ? u : 0) : make_float2(0.0f, 0.0f);
+                    const int lab = (in && u < U1) ? s_lab[u] : -1;
+                    // blank store unless this is the last row's inner cell (core.cu:284) or the label will
+                    // overwrite it anyway (label == blank: the label gradient wins, core.cu:383-390)
+                    const bool wb = in && !(t == T1 && u < U1) && lab != A.blank;
+                    const bool wl = in && u < U1;
+                    key[g] = in ? (t * U + u) : 0;              // cell index inside the lattice slab
+                    olf[g] = max(lab, 0) | (wb ? (1 << 29) : 0) | (wl ? (1 << 30) : 0);
                 }
+                const int odd = lane & 1;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const int t = tq[g], u = uq[g];
-                    if (t < 0) continue;
-                    float *row = A.grads + (slab + (int64_t)t * U + u) * V;
-                    if (!(t == T1 && u < U1)) row[A.blank] = gq[g].x;
-                    if (u < U1) row[s_lab[u]] = gq[g].y;   // after the blank: a label equal to blank wins (core.cu:383-390)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int src = 16 * h + (lane >> 1);
+                        const int k2 = __shfl_sync(0xffffffffu, key[g], src);
+                        const int f2 = __shfl_sync(0xffffffffu, olf[g], src);
+                        const float vb = __shfl_sync(0xffffffffu, gq[g].x, src);
+                        const float vl = __shfl_sync(0xffffffffu, gq[g].y, src);
+                        float *row = A.grads + (slab + (int64_t)k2) * V;
+                        const bool go = odd ? ((f2 >> 30) & 1) : ((f2 >> 29) & 1);
+                        if (go) row[odd ? (f2 & 0x1fffffff) : A.blank] = odd ? vl : vb;
+                    }
                 }
             }
         }
@@ -630,7 +647,7 @@ bool fused_plan(int N, int T, int U, FusedPlan *plan) {
     const int C = U <= 32 ? 1 : (U <= 64 ? 2 : (U <= 128 ? 4 : 8));
     int Wd = (U + C - 1) / C * C;
     if (Wd & 1) ++Wd;                                   // C == 1: keep the diagonal stride even
-    const int nd = T + Wd + 16;                         // diagonals + prefetch overshoot
+    const int nd = (T + Wd + 16 + 1) & ~1;              // diagonals + prefetch overshoot; even, so a plane is whole float4s
     const size_t smem = fused_smem_bytes(T, U, Wd, nd);
     if (smem > 220 * 1024) return false;
     if (((int64_t)T * U + kChunkCells - 1) / kChunkCells > kMaxChunks) return false;
