@@ -424,6 +424,16 @@ int rnnt_b200_compact_forward(void *stream, void *workspace, size_t workspace_by
     if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
     RNNT_TRY(launch_prefix(s, xn, yn, N, w.mem_pref, w.lab_pref, totals ? totals : w.totals), RNNT_STATUS_GATHER_FAILED);
     Problem p = {xn, yn, w.mem_pref, w.lab_pref, N, 0, 0, 1};
+    FusedPlan fplan;
+    if (max_T > 0 && max_U > 0 && want_fused(N, max_T, max_U, &fplan)) {
+        // small lattices: gather + wavefront + (cells,2) gradients + loc in one launch (no mismatch guard in the
+        // compact reference, core_compact.cu:347-358)
+        RNNT_TRY(launch_fused(s, resolve_kind(lse_mode, true), fplan, xs, ys, xn, yn, costs, nullptr,
+                              reinterpret_cast<float2 *>(pair_grads), nullptr, N, max_T, max_U, V, blank,
+                              fastemit_lambda, 0, 0, w.mem_pref, w.lab_pref, loc),
+                 RNNT_STATUS_WARP_FAILED);
+        return RNNT_STATUS_SUCCESS;
+    }
     DiagPlan dplan;
     if (max_T > 0 && max_U > 0 && want_diag(N, max_T, max_U, &dplan)) {
         // no mismatch guard in the compact reference (core_compact.cu:347-358)

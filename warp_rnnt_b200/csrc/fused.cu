@@ -165,7 +165,9 @@ __device__ __forceinline__ void sts_vec(uint32_t a, const float (&v)[C]) {
 
 struct FusedArgs {
     const float *lp;        // dense (N,T,U,V) or, pairs_in, (N,T,U,2)
-    const int *labels;      // (N,U-1)
+    const int *labels;      // (N,U-1); compact: (sum yn)
+    const int64_t *mem_pref, *lab_pref;   // compact layout: first cell / first label of lattice n (else null)
+    int64_t *loc;           // compact layout: label id per cell (core_compact.cu:424-431), or null
     const int *xn, *yn;
     float *costs;           // (N)
     float *grads;           // MODE 0: dense (N,T,U,V)
@@ -302,7 +304,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
 
     // rows of the padded slab this CTA fills / patches
     const int t0 = (int)((int64_t)T * slice / A.slices), t1 = (int)((int64_t)T * (slice + 1) / A.slices);
-    const int64_t slab = (int64_t)n * T * U;            // first cell of this lattice
+    // dense: lattice n is a padded (T,U) slab; compact: its Tn*Un cells are packed at mem_pref[n]
+    const bool compact = (A.mem_pref != nullptr);
+    const int64_t slab = compact ? A.mem_pref[n] : (int64_t)n * T * U;   // first cell of this lattice
+    const int RS = compact ? Un : U;                    // cells per lattice row in memory
+    const int64_t lab0 = compact ? A.lab_pref[n] : (int64_t)n * (U - 1);
+    // TMA rows need 16-byte aligned, 16-byte multiple rows: always true when chosen for the dense layout,
+    // per lattice in the compact layout
+    const bool use_tma = A.nbuf > 0 && (!compact || ((((slab * V) | ((int64_t)Un * V)) & 3) == 0));
 
     // ---- phase 0: sentinels, labels, gather
     if (tid == 0) { s_next = 0; s_bad = ok ? 0 : 1; }
@@ -322,7 +331,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
             reinterpret_cast<float4 *>(WLa)[k] = b4; reinterpret_cast<float4 *>(WLb)[k] = b4;
         }
         if (!A.pairs_in)
-            for (int u = tid; u < U1; u += kFusedThreads) s_lab[u] = A.labels[(int64_t)n * (U - 1) + u];
+            for (int u = tid; u < U1; u += kFusedThreads) s_lab[u] = A.labels[lab0 + u];
     }
     __syncthreads();
     stamp(1);
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     const int GW = A.gw;
     const int cells_n = ok ? Tn * Un : 0;
     const int nchunks = (cells_n + kChunkCells - 1) >> kChunkLog;
-    if (A.nbuf > 0) {
+    if (use_tma) {
         // TMA row gather: gather warp g owns row buffer g and stages order-rows g, g+nbuf, ...
         if (ok && lw >= 2 && lw < 2 + A.nbuf) {
             const int g = lw - 2;
@@ -352,7 +361,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
                 const int t = (k & 1) ? T1 - (k >> 1) : (k >> 1);   // rows alternate: top, bottom, top, ...
                 if (lane == 0) {
                     mbar_expect_tx(bar, bytes);
-                    bulk_load(buf_s, A.lp + (slab + (int64_t)t * U) * V, bytes, bar, pol_first);
+                    bulk_load(buf_s, A.lp + (slab + (int64_t)t * RS) * V, bytes, bar, pol_first);
                 }
                 while (!mbar_try_wait(bar, phase)) {}
                 phase ^= 1u;
@@ -393,7 +402,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
                 if (!in) { t = 0; u = 0; }
                 tt[g] = in ? t : -1;
                 uu[g] = u;
-                const int64_t cell = slab + (int64_t)t * U + u;
+                const int64_t cell = slab + (int64_t)t * RS + u;
                 vl[g] = kBigF;
                 if (A.pairs_in) {
                     const float2 w2 = ldg_hint2(reinterpret_cast<const float2 *>(A.lp) + cell, pol_first);
@@ -438,7 +447,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int i = min(i0 + 32 * k, T1);
-                    const int64_t cell = slab + (beta ? ((int64_t)(T1 - i) * U + U1) : ((int64_t)max(i - 1, 0) * U));
+                    const int64_t cell = slab + (beta ? ((int64_t)(T1 - i) * RS + U1) : ((int64_t)max(i - 1, 0) * RS));
                     v[k] = A.pairs_in ? __ldg(reinterpret_cast<const float2 *>(A.lp) + cell).x : __ldg(A.lp + cell * V + A.blank);
                     if (!beta && i == 0) v[k] = 0.0f;
                 }
@@ -467,7 +476,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         const uint32_t wl_a = (uint32_t)__cvta_generic_to_shared(beta ? WLb : WLa);
         const uint32_t out_a = (uint32_t)__cvta_generic_to_shared(beta ? BE : AL);
         GatherWait gwait;
-        gwait.flag = s_flag; gwait.Un = Un; gwait.Tn = Tn; gwait.ready = 0; gwait.lane = lane; gwait.gwn = A.nbuf;
+        gwait.flag = s_flag; gwait.Un = Un; gwait.Tn = Tn; gwait.ready = 0; gwait.lane = lane; gwait.gwn = use_tma ? A.nbuf : 0;
         stamp(3);
         sweep_diag<KIND, C>(wb_a, wl_a, out_a, Wd, ndiag, lane, first_col, pre, Tn, gwait, beta ? nullptr : trace);
         stamp(beta ? 5 : 4);
@@ -614,15 +623,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
                 }
             }
         }
-    } else if (A.pair_grads) {
-        const int cells = (t1 - t0) * U;
+    } else if (A.pair_grads || A.loc) {
+        // dense: every cell of rows [t0,t1) incl. padding (zeros); compact: the packed cells of rows < Tn
+        const int ncol = compact ? Un : U;
+        const int cells = ok ? max((compact ? min(t1, Tn) : t1) - t0, 0) * ncol : (compact ? 0 : (t1 - t0) * ncol);
 #pragma unroll 4
         for (int c = tid; c < cells; c += kFusedThreads) {
-            const int tt = c / U, u = c - tt * U;
+            const int tt = c / ncol, u = c - tt * ncol;
             const int t = t0 + tt;
             float2 gq = make_float2(0.0f, 0.0f);
             if (live && t < Tn && u < Un) gq = cell_grad(t, u);
-            A.pair_grads[slab + (int64_t)t * U + u] = gq;
+            const int64_t cell = slab + (int64_t)t * RS + u;
+            if (A.pair_grads) A.pair_grads[cell] = gq;
+            if (A.loc) A.loc[cell] = (u < U1) ? s_lab[u] : A.blank;   // last column: the blank (core_compact.cu:424-431)
         }
     }
     stamp(7);
@@ -688,8 +701,9 @@ static cudaError_t launch_fused_km(cudaStream_t s, const FusedArgs &a, size_t sm
 cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const float *lp, const int *labels,
                          const int *xn, const int *yn, float *costs, float *grads, float2 *pair_grads,
                          const float *scale, int N, int T, int U, int V, int blank, float lam, int pairs_in,
-                         int guard) {
+                         int guard, const int64_t *mem_pref, const int64_t *lab_pref, int64_t *loc) {
     FusedArgs a;
+    a.mem_pref = mem_pref; a.lab_pref = lab_pref; a.loc = loc;
     a.lp = lp; a.labels = labels; a.xn = xn; a.yn = yn; a.costs = costs; a.grads = grads; a.pair_grads = pair_grads;
     a.scale = scale; a.N = N; a.T = T; a.U = U; a.V = V; a.blank = blank; a.lam = lam; a.pairs_in = pairs_in;
     a.guard = guard; a.slices = (grads || pair_grads) ? plan.slices : 1; a.Wd = plan.W; a.nd = plan.ring;
@@ -737,7 +751,8 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
     const int C = plan.nw;
     if (kind == kFast)
         return dense ? launch_fused_km<kFast, 0>(s, a, smem, C) : launch_fused_km<kFast, 1>(s, a, smem, C);
-    // dense-layout exact flavour (the compact layout never takes the fused path)
+    if (kind == kExactCompact)                          // compact layout: (cells,2) gradients only
+        return launch_fused_km<kExactCompact, 1>(s, a, smem, C);
     return dense ? launch_fused_km<kExactDense, 0>(s, a, smem, C) : launch_fused_km<kExactDense, 1>(s, a, smem, C);
 }
 

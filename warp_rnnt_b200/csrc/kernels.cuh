@@ -43,7 +43,8 @@ void set_fused_trace(long long *buf);   // diagnostics: per-CTA phase stamps of 
 cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const float *lp, const int *labels,
                          const int *xn, const int *yn, float *costs, float *grads, float2 *pair_grads,
                          const float *scale, int N, int T, int U, int V, int blank, float lam, int pairs_in,
-                         int guard);
+                         int guard, const int64_t *mem_pref = nullptr, const int64_t *lab_pref = nullptr,
+                         int64_t *loc = nullptr);   // mem_pref != null: compact layout, T/U = max lengths
 
 // diag.cu -- general path on diagonal-major staged operands (any T, U <= 512)
 struct DiagPlan { int C, Wd, nd, t_cap; size_t smem; int64_t plane; size_t scratch_bytes; };
