@@ -43,6 +43,46 @@ __device__ __forceinline__ float2 cell_grads_ab(const Lattice &L, const ExpandSr
     return make_float2(gb, gl);
 }
 
+// (blank grad, label grad, label id or -1) of output row c -- the two non-zeros every emit flavour places
+template <int MODE>
+__device__ __forceinline__ void stage_row(const Problem &p, const ExpandSrc &src, int64_t c, int blank,
+                                          const FastDiv &divU, const FastDiv &divTU, float2 &g, int &lab) {
+    g = make_float2(0.0f, 0.0f);
+    lab = -1;
+    if (MODE == 2) {
+        // which sample? binary search in the inclusive cumsum (core_compact.cu:465-477)
+        int lo = 0, hi = p.N - 1;
+        while (lo <= hi) {
+            const int mid = lo + (hi - lo) / 2;
+            if (c >= (int64_t)src.cum_lens[mid]) lo = mid + 1; else hi = mid - 1;
+        }
+        const int n = min(lo, p.N - 1);
+        const float sc = src.scale ? src.scale[n] : 1.0f;
+        const float2 q = src.pg[c];
+        g = make_float2(q.x * sc, q.y * sc);
+        const int64_t l = src.loc[c];
+        lab = (l != (int64_t)blank) ? (int)l : -1;
+    } else {
+        uint32_t n, rem, t, u;
+        divTU.divmod((uint32_t)c, n, rem);
+        divU.divmod(rem, t, u);
+        if (MODE == 1) {
+            const float sc = src.scale ? src.scale[n] : 1.0f;
+            const float2 q = src.pg[c];
+            g = make_float2(q.x * sc, q.y * sc);
+            if ((int)u < p.U - 1) lab = src.labels[(int64_t)n * (p.U - 1) + u];
+        } else {
+            const Lattice L = get_lattice(p, (int)n);
+            const bool live = L.ok && !(src.bad && src.bad[n]);
+            if (live && (int)t < L.Tn && (int)u < L.Un) {
+                g = cell_grads_ab(L, src, (int)t, (int)u, src.betas[L.base]);
+                if (src.scale) { const float sc = src.scale[n]; g.x *= sc; g.y *= sc; }
+                if ((int)u < L.Un - 1) lab = src.labels[L.lab_base + u];
+            }
+        }
+    }
+}
+
 // MODE 0: dense layout, source = alpha/beta/pairs (forward)            label overrides blank
 // MODE 1: dense layout, source = pair grads (gather=True backward)     label adds to blank (scatter_add)
 // MODE 2: compact layout, source = pair grads + loc (compact backward) label written iff loc != blank
@@ -59,41 +99,9 @@ k_expand(Problem p, ExpandSrc src, float *__restrict__ out, int64_t cells, int V
         __syncthreads();  // previous chunk's sweep is done with s_g / s_lab
         // ---- phase 1: stage the rows' non-zeros
         for (int r = threadIdx.x; r < rows; r += kExpandThreads) {
-            const int64_t c = r0 + r;
-            float2 g = make_float2(0.0f, 0.0f);
-            int lab = -1;
-            if (MODE == 2) {
-                // which sample? binary search in the inclusive cumsum (core_compact.cu:465-477)
-                int lo = 0, hi = p.N - 1;
-                while (lo <= hi) {
-                    const int mid = lo + (hi - lo) / 2;
-                    if (c >= (int64_t)src.cum_lens[mid]) lo = mid + 1; else hi = mid - 1;
-                }
-                const int n = min(lo, p.N - 1);
-                const float sc = src.scale ? src.scale[n] : 1.0f;
-                const float2 q = src.pg[c];
-                g = make_float2(q.x * sc, q.y * sc);
-                const int64_t l = src.loc[c];
-                lab = (l != (int64_t)blank) ? (int)l : -1;
-            } else {
-                uint32_t n, rem, t, u;
-                divTU.divmod((uint32_t)c, n, rem);
-                divU.divmod(rem, t, u);
-                if (MODE == 1) {
-                    const float sc = src.scale ? src.scale[n] : 1.0f;
-                    const float2 q = src.pg[c];
-                    g = make_float2(q.x * sc, q.y * sc);
-                    if ((int)u < p.U - 1) lab = src.labels[(int64_t)n * (p.U - 1) + u];
-                } else {
-                    const Lattice L = get_lattice(p, (int)n);
-                    const bool live = L.ok && !(src.bad && src.bad[n]);
-                    if (live && (int)t < L.Tn && (int)u < L.Un) {
-                        g = cell_grads_ab(L, src, (int)t, (int)u, src.betas[L.base]);
-                        if (src.scale) { const float sc = src.scale[n]; g.x *= sc; g.y *= sc; }
-                        if ((int)u < L.Un - 1) lab = src.labels[L.lab_base + u];
-                    }
-                }
-            }
+            float2 g;
+            int lab;
+            stage_row<MODE>(p, src, r0 + r, blank, divU, divTU, g, lab);
             s_g[r] = g;
             s_lab[r] = lab;
         }
