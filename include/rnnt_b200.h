@@ -120,7 +120,8 @@ int rnnt_b200_gather_backward(void *stream, const float *pair_grads, const int *
  *   pair_grads (STU,2) out or NULL (forward only = the reference's required_grad=false)
  *   loc (STU) i64 out or NULL: label id per cell, blank on each sample's last column
  *   totals (4) i32 out or NULL: {sum xn*(yn+1), sum yn, max xn, max yn+1} for host validation
- *   max_T, max_U: launch-shaping hints (upper bounds of xn and yn+1), 0 = unknown */
+ *   max_T, max_U: launch-shaping hints, UPPER BOUNDS of xn and yn+1 (0 = unknown: general kernels).  With
+ *   hints small lattices take the single fused kernel; a sample exceeding the hints gets cost NaN. */
 int rnnt_b200_compact_forward(void *stream, void *workspace, size_t workspace_bytes,
                               const float *xs, const int *ys, const int *xn, const int *yn,
                               float *costs, float *pair_grads, int64_t *loc, int *totals,

@@ -675,12 +675,25 @@ bool fused_plan(int N, int T, int U, FusedPlan *plan) {
 }
 
 template <int KIND, int MODE, int C>
-static cudaError_t launch_fused_kmc(cudaStream_t s, const FusedArgs &a, size_t smem) {
+static cudaError_t launch_fused_kmc(cudaStream_t s, FusedArgs a, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_fused<KIND, MODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedMaxDynSmem);
         if (e != cudaSuccess) return e;
         attr_set = true;
+    }
+    if (a.slices > 1) {
+        // CTAs per lattice: fill every SM with what is actually co-resident (registers can forbid the second
+        // CTA that shared memory would allow; a second, partial wave costs more than it brings)
+        static size_t occ_smem = ~(size_t)0;
+        static int occ = 1, sms = 148;
+        if (occ_smem != smem) {
+            int dev = 0, n = 1;
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fused<KIND, MODE, C>, kFusedThreads, smem) == cudaSuccess && n >= 1) occ = n;
+            occ_smem = smem;
+        }
+        a.slices = max(1, min(a.slices, (occ * sms) / a.N));
     }
     dim3 grid(a.slices, a.N);
     k_fused<KIND, MODE, C><<<grid, kFusedThreads, smem, s>>>(a);
@@ -689,7 +702,7 @@ static cudaError_t launch_fused_kmc(cudaStream_t s, const FusedArgs &a, size_t s
 }
 
 template <int KIND, int MODE>
-static cudaError_t launch_fused_km(cudaStream_t s, const FusedArgs &a, size_t smem, int C) {
+static cudaError_t launch_fused_km(cudaStream_t s, const FusedArgs &a, size_t smem, int C) {   // (a is copied per launch)
     switch (C) {
         case 1: return launch_fused_kmc<KIND, MODE, 1>(s, a, smem);
         case 2: return launch_fused_kmc<KIND, MODE, 2>(s, a, smem);
