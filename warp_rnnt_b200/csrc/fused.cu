@@ -577,50 +577,52 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     };
     if (MODE == 0) {
         if (live) {
+            // One ITEM per lane and pass: lane 2k patches the blank gradient and lane 2k+1 the label gradient of
+            // the same cell -- one expf each, and a store instruction covers 16 adjacent cells (the LSU makes one
+            // pass per 128-byte line touched, a cell is 4*V bytes wide).  Four items in flight per thread: all
+            // shared-memory reads and expf chains first, then the stores.
             const int r0 = t0, r1 = min(t1, Tn);
-            const int cells = (r1 - r0) * Un;
+            const int items = (r1 - r0) * Un * 2;
             const float inv = 1.0f / (float)Un;
-            // four cells per thread and pass: all shared-memory reads and both expf chains of the four
-            // cells first (independent, so they overlap), then the scattered stores.  A store instruction
-            // costs the LSU one pass per 128-byte line it touches, and a cell is 4*V bytes wide, so the
-            // stores are issued with lanes (2k, 2k+1) = (blank, label) of ONE cell: 16 adjacent cells per
-            // instruction (~half the lines of 32 blanks followed by 32 labels).
+            const int which = tid & 1;                  // 0 = blank, 1 = label (kFusedThreads is even)
+            const float *wplane = which ? WLb : WBb;
             constexpr int G = 4;
-            for (int base = warp * 32; base < cells; base += kFusedThreads * G) {   // warp-uniform trip count
-                float2 gq[G];
-                int key[G], olf[G];
+            for (int base = tid; base < items; base += kFusedThreads * G) {
+                float val[G];
+                int64_t off[G];
+                bool go[G];
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const int c = base + g * kFusedThreads + lane;
+                    const int q = base + g * kFusedThreads;
+                    const bool in = q < items;
+                    const int c = in ? (q >> 1) : 0;
                     int tt = (int)(((float)c + 0.5f) * inv);
                     int u = c - tt * Un;
                     if (u < 0) { --tt; u += Un; } else if (u >= Un) { ++tt; u -= Un; }
-                    const bool in = c < cells;
                     const int t = r0 + tt;
-                    gq[g] = in ? cell_grad(t, in ? u : 0) : make_float2(0.0f, 0.0f);
-                    const int lab = (in && u < U1) ? s_lab[u] : -1;
-                    // blank store unless this is the last row's inner cell (core.cu:284) or the label will
-                    // overwrite it anyway (label == blank: the label gradient wins, core.cu:383-390)
-                    const bool wb = in && !(t == T1 && u < U1) && lab != A.blank;
-                    const bool wl = in && u < U1;
-                    key[g] = in ? (t * U + u) : 0;              // cell index inside the lattice slab
-                    olf[g] = max(lab, 0) | (wb ? (1 << 29) : 0) | (wl ? (1 << 30) : 0);
+                    const bool last_t = (t == T1), last_u = (u == U1);
+                    const int ib = idxB(t, u);
+                    // same operation order as core.cu:284-294 (blank) and :319-331 (label):
+                    //   blank: a = alpha[t,u] (+ beta[t+1,u] unless last row);  label: a = alpha[t,u] + beta[t,u+1]
+                    const bool add_beta = which ? !last_u : !last_t;
+                    float a = AL[idxA(t, u)];
+                    if (add_beta) a += BE[ib - Wd - which];   // beta[t+1,u]: previous diagonal, same column; beta[t,u+1]: one column before
+                    a = expf(a + wplane[ib] - b00);
+                    // (1. + lambda) * a is a double multiply in the reference (core.cu:327-329); with lambda == 0
+                    // it returns a unchanged, so the fp64 round trip is skipped without changing a bit
+                    if (which && has_lam) a = (float)((1.0 + (double)A.lam) * (double)a);
+                    float v = -a;
+                    if (A.scale) v *= sc;
+                    val[g] = v;
+                    const int lab = last_u ? -1 : s_lab[u];
+                    // blank: every cell except the last row's inner cells (core.cu:284), and not where the label
+                    // store lands on the same element (label == blank: the label gradient wins, core.cu:383-390)
+                    go[g] = in && (which ? !last_u : (!(last_t && !last_u) && lab != A.blank));
+                    off[g] = (slab + (int64_t)t * RS + u) * V + (which ? max(lab, 0) : A.blank);
                 }
-                const int odd = lane & 1;
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int src = 16 * h + (lane >> 1);
-                        const int k2 = __shfl_sync(0xffffffffu, key[g], src);
-                        const int f2 = __shfl_sync(0xffffffffu, olf[g], src);
-                        const float vb = __shfl_sync(0xffffffffu, gq[g].x, src);
-                        const float vl = __shfl_sync(0xffffffffu, gq[g].y, src);
-                        float *row = A.grads + (slab + (int64_t)k2) * V;
-                        const bool go = odd ? ((f2 >> 30) & 1) : ((f2 >> 29) & 1);
-                        if (go) row[odd ? (f2 & 0x1fffffff) : A.blank] = odd ? vl : vb;
-                    }
-                }
+                for (int g = 0; g < G; ++g)
+                    if (go[g]) A.grads[off[g]] = val[g];
             }
         }
     } else if (A.pair_grads || A.loc) {
