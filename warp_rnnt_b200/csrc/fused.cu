@@ -116,6 +116,15 @@ struct GatherWait {
     const int *flag;
     int Un, Tn, lane, gwn;  // gwn > 0: TMA row gather with gwn warps
     int ready;              // chunks [0, ready) / order-rows [0, ready) are known complete
+    int m_ok;               // rows(m) is known to hold for every m <= m_ok (one compare on the per-step path)
+    __device__ __forceinline__ void ensure(int m) {
+        if (m > m_ok) {
+            rows(m);
+            // order-rows known complete -> largest m with min(2m+1, Tn-1) < rows_done
+            const int rows_done = gwn > 0 ? ready : min(Tn, (ready << kChunkLog) / Un);
+            m_ok = (rows_done >= Tn) ? 0x7fffffff : ((rows_done - 2) >> 1);
+        }
+    }
     __device__ __forceinline__ void rows(int m) {
         const int k = min(2 * m + 1, Tn - 1);
         if (gwn > 0) {
@@ -181,6 +190,7 @@ struct FusedArgs {
     int Wd;                 // staged row stride (floats) = C * ceil(U / C), even
     int nd;                 // staged rows (diagonals) allocated = T + Wd + 16
     int gw;                 // warps that gather (of the 14 non-wavefront warps); MODE 0: the rest start the zero-fill at once
+    int dbg;                // experiments only (RNNT_B200_DEBUG_FILL)
     int tma_fill;           // MODE 0: zero-fill with bulk shared->global copies (else 256-bit STG)
     long long *trace;       // optional per-CTA phase stamps (clock64), 8 per CTA; null = off
 };
@@ -195,11 +205,24 @@ struct FusedArgs {
 //   cells past the last row / column only ever feed other out-of-lattice slots.
 // Column j at diagonal d reads its own previous value (row edge) and column j-1's previous value
 // (column edge): inside a lane that is a register, across lanes one __shfl_up of the lane's last column.
+// __shfl_up_sync(full, v, 1) as a volatile asm: keeps the shuffle in program order with the (volatile)
+// shared-memory loads/stores of the loop.  Left free, the compiler batches three steps' LDS/STS in front of
+// the fourth shuffle and then copies the freshly loaded operands into place -- register moves that wait
+// for the load they follow, on the dependent chain (exact LSE: 158 vs 125 ns per step).
+__device__ __forceinline__ float shfl_up1_ordered(float v) {
+    float r;
+    asm volatile("shfl.sync.up.b32 %0, %1, 1, 0, 0xffffffff;" : "=f"(r) : "f"(v) : "memory");
+    return r;
+}
+
 template <int KIND, int C>
 __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t out, int Wd, int ndiag, int lane,
                                            int first_col, const float *pre, int pre_rows, GatherWait gw,
-                                           long long *trace) {
-    constexpr int P = (C <= 2) ? 4 : 2;                       // diagonals of operand prefetch
+                                           long long *trace, uint32_t scratch) {
+    // diagonals of operand prefetch = steps per loop iteration.  Exact LSE: ONE step per iteration -- inside a
+    // multi-step block ptxas runs the lane's C chains of all but the first step one after the other instead of
+    // interleaved (160 vs 125 ns per step); a step outlasts the LDS latency several times, so P = 1 suffices
+    constexpr int P = (KIND != kFast) ? 1 : ((C <= 2) ? 4 : 2);
     float val[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) val[c] = (C * lane + c == first_col) ? 0.0f : kBigF;
@@ -214,9 +237,13 @@ __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t ou
     uint32_t a_wb = wb + off, a_wl = wl + off, a_out = out + off;
     // exact mode: the first real column is taken from the reference-order prefix scan (core.cu:92-110)
     const int l0 = first_col / C, c0 = first_col - l0 * C;
-    bool own[C];                                              // this register holds the first real column
+    // Predicate registers are scarce (7 per thread) and each exact-LSE chain keeps 3 alive; with more in the
+    // loop ptxas runs the lane's C chains one after the other instead of interleaved (160 vs 125 ns per step
+    // at C = 2).  So the column override is a bitwise select on a mask, and lanes past the staged row store to a
+    // scratch slot instead of being predicated off.
+    uint32_t own[C];                                          // all-ones where this register holds the first real column
 #pragma unroll
-    for (int c = 0; c < C; ++c) own[c] = (KIND != kFast) && lane == l0 && c == c0;
+    for (int c = 0; c < C; ++c) own[c] = ((KIND != kFast) && lane == l0 && c == c0) ? 0xffffffffu : 0u;
     const uint32_t a_pre = (uint32_t)__cvta_generic_to_shared(pre);
     auto pre_at = [&](int d) -> float {                      // scan value for diagonal d (clamped; unused when out of range)
         const int i = min(max(d - first_col, 0), pre_rows - 1);
@@ -224,9 +251,14 @@ __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t ou
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a_pre + 4u * (uint32_t)i) : "memory");
         return v;
     };
-    const bool in_row = C * lane < Wd;                         // (results are written in place over operands, see k_fused)
+    // results are written in place over operands (see k_fused): lanes past the staged row must not spill into
+    // the next one -- they store to `scratch` (4*C bytes per lane) instead
+    const bool in_row = C * lane < Wd;
+    if (!in_row) a_out = scratch + off;
+    uint32_t stride_out = in_row ? stride : 0u;
+    asm volatile("" : "+r"(stride_out));
     float b[P][C], l[P][C], pv[P];
-    gw.rows(P - 1);                                           // diagonals 0..P-1 touch rows <= P-1
+    gw.ensure(P - 1);                                         // diagonals 0..P-1 touch rows <= P-1
 #pragma unroll
     for (int k = 0; k < P; ++k) {
         lds_vec<C>(a_wb, b[k]);
@@ -236,25 +268,28 @@ __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t ou
         a_wl += stride;
     }
     for (int d0 = 0; d0 < ndiag; d0 += P) {
-        if (trace && lane == 0 && (d0 & 31) == 0 && d0 < 256) trace[8 + (d0 >> 5)] = clock64();   // diagnostics only
-        gw.rows(d0 + 2 * P - 1);                               // the gather has staged every row this iteration prefetches
+        if ((d0 & 31) == 0 && trace && lane == 0 && d0 < 256) trace[8 + (d0 >> 5)] = clock64();   // diagnostics only
+        gw.ensure(d0 + 2 * P - 1);                             // the gather has staged every row this iteration prefetches
 #pragma unroll
         for (int k = 0; k < P; ++k) {
-            const float left = __shfl_up_sync(0xffffffffu, val[C - 1], 1);   // lane 0 gets its own value: wl = kBig there
+            const float left = shfl_up1_ordered(val[C - 1]);   // lane 0 gets its own value: wl = kBig there
             float nv[C];
             nv[0] = lse<KIND>(val[0] + b[k][0], left + l[k][0]);
 #pragma unroll
             for (int c = 1; c < C; ++c) nv[c] = lse<KIND>(val[c] + b[k][c], val[c - 1] + l[k][c]);
             if (KIND != kFast) {
                 const int i = d0 + k - first_col;              // row of the first real column on this diagonal
-                const bool in = (i >= 1) && (i < pre_rows);
+                const uint32_t in = ((i >= 1) && (i < pre_rows)) ? 0xffffffffu : 0u;
 #pragma unroll
-                for (int c = 0; c < C; ++c) nv[c] = (own[c] && in) ? pv[k] : nv[c];
+                for (int c = 0; c < C; ++c) {
+                    const uint32_t m = own[c] & in;
+                    nv[c] = __uint_as_float((__float_as_uint(nv[c]) & ~m) | (__float_as_uint(pv[k]) & m));
+                }
             }
 #pragma unroll
             for (int c = 0; c < C; ++c) val[c] = nv[c];
-            if (in_row) sts_vec<C>(a_out, val);              // lanes past the staged row must not spill into the next one
-            a_out += stride;
+            sts_vec<C>(a_out, val);                          // (lanes past the staged row: scratch slot, stride 0)
+            a_out += stride_out;
             lds_vec<C>(a_wb, b[k]);                            // operands P diagonals ahead (rows past ndiag are allocated)
             lds_vec<C>(a_wl, l[k]);
             if (KIND != kFast) pv[k] = pre_at(d0 + k + P);
@@ -281,15 +316,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     float *WLa = WBa + plane;                           // alpha: label edge into (t,u)   at [t+u][u]
     float *WBb = WLa + plane;                           // beta : blank edge out of (t,u) at [d'][j'], j' = Wd-1-u, d' = (T1-t)+j'
     float *WLb = WBb + plane;                           // beta : label edge out of (t,u) at [d'][j']
-    float *AL = WLa;                                    // alpha[t,u] at [t+u][u]: IN PLACE over its label edges -- the
+    float *AL = (A.dbg == 5) ? WLb + 2 * plane : WLa;   // alpha[t,u] at [t+u][u]: IN PLACE over its label edges -- the
                                                         // wavefront has read slot [d][j] P steps before it writes it;
                                                         // phase 2 takes the log-probs from the beta-side copies
     float *BE = WLb + plane;                            // beta[t,u]  at [d'][j']
-    float *preA = BE + plane;                           // [T] exact-mode column scans
+    float *preA = BE + plane * (A.dbg == 5 ? 2 : 1);   // [T] exact-mode column scans
     float *preB = preA + T;
     int *s_lab = reinterpret_cast<int *>(preB + T);     // [U]
     // zero buffer for the bulk fill: the last kZeroBytes of the dynamic allocation (128-byte aligned)
     float *zbuf = reinterpret_cast<float *>(smem_raw + A.zoff);
+    __shared__ __align__(16) float s_scratch[2][256];   // wavefront lanes past the staged row store here
     __shared__ int s_next;                              // fill work counter
     __shared__ int s_bad;
     __shared__ int s_flag[kMaxChunks];                  // gather chunk q staged / rows finished by gather warp g
@@ -474,11 +510,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         }
         const uint32_t wb_a = (uint32_t)__cvta_generic_to_shared(beta ? WBb : WBa);
         const uint32_t wl_a = (uint32_t)__cvta_generic_to_shared(beta ? WLb : WLa);
-        const uint32_t out_a = (uint32_t)__cvta_generic_to_shared(beta ? BE : AL);
+        const uint32_t out_a = (uint32_t)__cvta_generic_to_shared(beta ? BE : AL);   // (AL == WLa unless dbg 5)
         GatherWait gwait;
-        gwait.flag = s_flag; gwait.Un = Un; gwait.Tn = Tn; gwait.ready = 0; gwait.lane = lane; gwait.gwn = use_tma ? A.nbuf : 0;
+        gwait.flag = s_flag; gwait.Un = Un; gwait.Tn = Tn; gwait.ready = 0; gwait.lane = lane; gwait.gwn = use_tma ? A.nbuf : 0; gwait.m_ok = -1;
         stamp(3);
-        sweep_diag<KIND, C>(wb_a, wl_a, out_a, Wd, ndiag, lane, first_col, pre, Tn, gwait, beta ? nullptr : trace);
+        sweep_diag<KIND, C>(wb_a, wl_a, out_a, Wd, ndiag, lane, first_col, pre, Tn, gwait, beta ? nullptr : trace,
+                            (uint32_t)__cvta_generic_to_shared(&s_scratch[lw][0]));
         stamp(beta ? 5 : 4);
     }
     if (MODE == 0) {
@@ -492,16 +529,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         constexpr int kChunk = 8192;                    // floats per chunk
         const int64_t nfill = (a1 - a0 + kChunk - 1) / kChunk;
         if (A.tma_fill) {
-            if (lane == 0) {
+            const bool issuer = (A.dbg == 2) ? (lw == 2 || lw == 3) : (A.dbg == 3 ? lw == 2 : true);
+            if (lane == 0 && issuer && A.dbg != 1) {
                 const uint64_t pol = policy_evict_last();
                 const uint32_t zs = (uint32_t)__cvta_generic_to_shared(zbuf);
+                const int piece = (A.dbg == 4) ? 512 : kZeroBytes / 4;     // floats per bulk copy
                 for (;;) {
                     const int c = atomicAdd(&s_next, 1);
                     if (c >= nfill) break;
                     const int64_t b = a0 + (int64_t)c * kChunk;
                     const int64_t e = min(a1, b + kChunk);
-                    for (int64_t f = b; f < e; f += kZeroBytes / 4)
-                        bulk_store(g + f, zs, (uint32_t)(min(e - f, (int64_t)(kZeroBytes / 4)) * 4), pol);
+                    for (int64_t f = b; f < e; f += piece)
+                        bulk_store(g + f, zs, (uint32_t)(min(e - f, (int64_t)piece) * 4), pol);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the zeros have landed ...
@@ -644,7 +683,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
 }
 
 // ---- host side -------------------------------------------------------------------------------
-constexpr int kFusedMaxDynSmem = 225 * 1024;           // 227 KB per CTA minus the kernel's static shared memory
+constexpr int kFusedMaxDynSmem = 223 * 1024;           // 227 KB per CTA minus the kernel's static shared memory
 static long long *g_fused_trace = nullptr;             // diagnostics: see rnnt_b200_debug_fused_trace
 void set_fused_trace(long long *buf) { g_fused_trace = buf; }
 
@@ -735,10 +774,13 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
         a.gw = gw_env ? gw_env : kFusedThreads / 32 - 2;
         if (!grads) a.gw = kFusedThreads / 32 - 2;      // nothing to fill: everyone gathers
     }
+    { const char *e = getenv("RNNT_B200_DEBUG_FILL"); a.dbg = e ? atoi(e) : 0; }
     a.zoff = (int)(plan.smem - kZeroBytes);
+    size_t extra = 0;
+    if (a.dbg == 5) { extra = ((size_t)plan.ring * plan.W * 4 + 127) / 128 * 128; a.zoff += (int)extra; }
     // TMA row gather when a lattice row (U*V floats) is a 16-byte multiple at a 16-byte aligned address and
     // at least four row buffers fit behind the planes (RNNT_B200_GATHER=ldg forces the LDG gather)
-    size_t smem = plan.smem;
+    size_t smem = plan.smem + extra;
     a.nbuf = 0; a.row_off = 0; a.row_stride = 0;
     {
         static int want_tma = -1;
@@ -748,12 +790,12 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
         // keep two CTAs per SM where the plan counted on them
         const size_t cap = (plan.smem <= 110 * 1024) ? (size_t)113 * 1024 : (size_t)kFusedMaxDynSmem;
         if (want_tma && !pairs_in && (row % 16) == 0 && (reinterpret_cast<uintptr_t>(lp) % 16) == 0 && row <= 32 * 1024 &&
-            plan.smem + 4 * stride <= cap) {
-            const int nb = (int)((cap - plan.smem) / stride);
+            plan.smem + extra + 4 * stride <= cap) {
+            const int nb = (int)((cap - plan.smem - extra) / stride);
             a.nbuf = nb < kMaxRowBufs ? nb : kMaxRowBufs;
-            a.row_off = (int)plan.smem;
+            a.row_off = (int)(plan.smem + extra);
             a.row_stride = (int)stride;
-            smem = plan.smem + (size_t)a.nbuf * stride;
+            smem = plan.smem + extra + (size_t)a.nbuf * stride;
         }
     }
     {
