@@ -69,8 +69,7 @@ uint64_t rnnt_b200_launch_count(void);
 /* Diagnostics: when `buf` is non-NULL the fused small-lattice kernel records, per CTA (grid order
  * blockIdx.y * gridDim.x + blockIdx.x), sixteen clock64() stamps (latest arrival of each phase):
  * 0 start, 1 sentinels set, 2 gather done, 3 wavefront start, 4 alpha done, 5 beta done, 6 zero-fill
- * done, 7 kernel end, 8+i the alpha wavefront reaching diagonal 32*i.  `buf` is device memory, 16 * CTAs
- * int64, zeroed by the caller.  NULL = off. */
+ * done, 7 kernel end (8..15 reserved).  `buf` is device memory, 16 * CTAs int64, zeroed by the caller.  NULL = off. */
 void rnnt_b200_debug_fused_trace(void *buf);
 
 /* ------------------------------------------------------------------------------------------

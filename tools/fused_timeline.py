@@ -15,7 +15,7 @@ import torch  # noqa: E402
 import warp_rnnt_b200 as w  # noqa: E402
 
 SHAPES = {"c2": (128, 150, 40, 28), "c3": (32, 150, 20, 5000), "c1": (1, 150, 40, 28)}
-NAMES = ["start", "sentinels", "gather_done", "sweep_start", "alpha_done", "beta_done", "fill_done", "end"] + ["a_d%d" % (32 * i) for i in range(8)]
+NAMES = ["start", "sentinels", "gather_done", "sweep_start", "alpha_done", "beta_done", "fill_done", "end"]
 
 
 def sm_mhz():
@@ -60,7 +60,7 @@ def main():
         mhz = max(mhz, sm_mhz())
         tr = trace.view(-1, 16).cpu()
         tr = tr[tr[:, 0] > 0]
-        rel = (tr - tr[:, :1]).clamp(min=0).double() / mhz          # cycles / MHz = us
+        rel = (tr[:, :8] - tr[:, :1]).clamp(min=0).double() / mhz          # cycles / MHz = us
         med = rel.median(dim=0).values.tolist()
         mx = rel.max(dim=0).values.tolist()
         out[mode] = {"ctas": int(tr.shape[0]), "sm_mhz": mhz, "event_us": e0.elapsed_time(e1) * 1e3,

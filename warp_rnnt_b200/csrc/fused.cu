@@ -218,11 +218,8 @@ __device__ __forceinline__ float shfl_up1_ordered(float v) {
 template <int KIND, int C>
 __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t out, int Wd, int ndiag, int lane,
                                            int first_col, const float *pre, int pre_rows, GatherWait gw,
-                                           long long *trace, uint32_t scratch) {
-    // diagonals of operand prefetch = steps per loop iteration.  Exact LSE: ONE step per iteration -- inside a
-    // multi-step block ptxas runs the lane's C chains of all but the first step one after the other instead of
-    // interleaved (160 vs 125 ns per step); a step outlasts the LDS latency several times, so P = 1 suffices
-    constexpr int P = (KIND != kFast) ? 1 : ((C <= 2) ? 4 : 2);
+                                           uint32_t scratch) {
+    constexpr int P = (C <= 2) ? 4 : 2;                       // diagonals of operand prefetch = steps per loop iteration
     float val[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) val[c] = (C * lane + c == first_col) ? 0.0f : kBigF;
@@ -267,9 +264,16 @@ __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t ou
         a_wb += stride;
         a_wl += stride;
     }
-    for (int d0 = 0; d0 < ndiag; d0 += P) {
-        if ((d0 & 31) == 0 && trace && lane == 0 && d0 < 256) trace[8 + (d0 >> 5)] = clock64();   // diagnostics only
-        gw.ensure(d0 + 2 * P - 1);                             // the gather has staged every row this iteration prefetches
+    // Exact LSE: ptxas interleaves the lane's C chains in every step of the unrolled body except the last one
+    // before the back-edge (and in none of them if the loop also contains a conditional store, e.g. a trace
+    // stamp) -- so the body is 2P steps long: 7 of 8 steps run at ~125 ns instead of 160 ns.
+    // tools/sass_check.py watches this.
+    constexpr int H = (KIND != kFast) ? 2 : 1;                 // groups of P steps per iteration
+    for (int d00 = 0; d00 < ndiag; d00 += H * P) {
+        gw.ensure(d00 + (H + 1) * P - 1);                      // the gather has staged every row this iteration prefetches
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const int d0 = d00 + h * P;
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             const float left = shfl_up1_ordered(val[C - 1]);   // lane 0 gets its own value: wl = kBig there
@@ -296,6 +300,7 @@ __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t ou
             a_wb += stride;
             a_wl += stride;
         }
+      }
     }
 }
 
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros -> async-proxy reads
     }
     if (ok) {
-        const int used = (Tn + Wd + 8) * Wd;            // diagonals any sweep or its prefetch can touch
+        const int used = (Tn + Wd + 16) * Wd;           // diagonals any sweep or its prefetch can touch
         const int lim4 = min((used + 3) >> 2, (int)(plane >> 2));   // planes are whole float4s (nd, Wd even)
         const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), b4 = make_float4(kBigF, kBigF, kBigF, kBigF);
         for (int k = tid; k < lim4; k += kFusedThreads) {
@@ -514,7 +519,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         GatherWait gwait;
         gwait.flag = s_flag; gwait.Un = Un; gwait.Tn = Tn; gwait.ready = 0; gwait.lane = lane; gwait.gwn = use_tma ? A.nbuf : 0; gwait.m_ok = -1;
         stamp(3);
-        sweep_diag<KIND, C>(wb_a, wl_a, out_a, Wd, ndiag, lane, first_col, pre, Tn, gwait, beta ? nullptr : trace,
+        sweep_diag<KIND, C>(wb_a, wl_a, out_a, Wd, ndiag, lane, first_col, pre, Tn, gwait,
                             (uint32_t)__cvta_generic_to_shared(&s_scratch[lw][0]));
         stamp(beta ? 5 : 4);
     }
