@@ -190,7 +190,6 @@ struct FusedArgs {
     int Wd;                 // staged row stride (floats) = C * ceil(U / C), even
     int nd;                 // staged rows (diagonals) allocated = T + Wd + 16
     int gw;                 // warps that gather (of the 14 non-wavefront warps); MODE 0: the rest start the zero-fill at once
-    int dbg;                // experiments only (RNNT_B200_DEBUG_FILL)
     int tma_fill;           // MODE 0: zero-fill with bulk shared->global copies (else 256-bit STG)
     long long *trace;       // optional per-CTA phase stamps (clock64), 8 per CTA; null = off
 };
@@ -321,11 +320,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     float *WLa = WBa + plane;                           // alpha: label edge into (t,u)   at [t+u][u]
     float *WBb = WLa + plane;                           // beta : blank edge out of (t,u) at [d'][j'], j' = Wd-1-u, d' = (T1-t)+j'
     float *WLb = WBb + plane;                           // beta : label edge out of (t,u) at [d'][j']
-    float *AL = (A.dbg == 5) ? WLb + 2 * plane : WLa;   // alpha[t,u] at [t+u][u]: IN PLACE over its label edges -- the
+    float *AL = WLa;                                    // alpha[t,u] at [t+u][u]: IN PLACE over its label edges -- the
                                                         // wavefront has read slot [d][j] P steps before it writes it;
                                                         // phase 2 takes the log-probs from the beta-side copies
     float *BE = WLb + plane;                            // beta[t,u]  at [d'][j']
-    float *preA = BE + plane * (A.dbg == 5 ? 2 : 1);   // [T] exact-mode column scans
+    float *preA = BE + plane;                           // [T] exact-mode column scans
     float *preB = preA + T;
     int *s_lab = reinterpret_cast<int *>(preB + T);     // [U]
     // zero buffer for the bulk fill: the last kZeroBytes of the dynamic allocation (128-byte aligned)
@@ -515,7 +514,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         }
         const uint32_t wb_a = (uint32_t)__cvta_generic_to_shared(beta ? WBb : WBa);
         const uint32_t wl_a = (uint32_t)__cvta_generic_to_shared(beta ? WLb : WLa);
-        const uint32_t out_a = (uint32_t)__cvta_generic_to_shared(beta ? BE : AL);   // (AL == WLa unless dbg 5)
+        const uint32_t out_a = (uint32_t)__cvta_generic_to_shared(beta ? BE : AL);
         GatherWait gwait;
         gwait.flag = s_flag; gwait.Un = Un; gwait.Tn = Tn; gwait.ready = 0; gwait.lane = lane; gwait.gwn = use_tma ? A.nbuf : 0; gwait.m_ok = -1;
         stamp(3);
@@ -534,11 +533,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         constexpr int kChunk = 8192;                    // floats per chunk
         const int64_t nfill = (a1 - a0 + kChunk - 1) / kChunk;
         if (A.tma_fill) {
-            const bool issuer = (A.dbg == 2) ? (lw == 2 || lw == 3) : (A.dbg == 3 ? lw == 2 : true);
-            if (lane == 0 && issuer && A.dbg != 1) {
+            if (lane == 0) {
                 const uint64_t pol = policy_evict_last();
                 const uint32_t zs = (uint32_t)__cvta_generic_to_shared(zbuf);
-                const int piece = (A.dbg == 4) ? 512 : kZeroBytes / 4;     // floats per bulk copy
+                constexpr int piece = kZeroBytes / 4;   // floats per bulk copy
                 for (;;) {
                     const int c = atomicAdd(&s_next, 1);
                     if (c >= nfill) break;
@@ -779,13 +777,10 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
         a.gw = gw_env ? gw_env : kFusedThreads / 32 - 2;
         if (!grads) a.gw = kFusedThreads / 32 - 2;      // nothing to fill: everyone gathers
     }
-    { const char *e = getenv("RNNT_B200_DEBUG_FILL"); a.dbg = e ? atoi(e) : 0; }
     a.zoff = (int)(plan.smem - kZeroBytes);
-    size_t extra = 0;
-    if (a.dbg == 5) { extra = ((size_t)plan.ring * plan.W * 4 + 127) / 128 * 128; a.zoff += (int)extra; }
     // TMA row gather when a lattice row (U*V floats) is a 16-byte multiple at a 16-byte aligned address and
     // at least four row buffers fit behind the planes (RNNT_B200_GATHER=ldg forces the LDG gather)
-    size_t smem = plan.smem + extra;
+    size_t smem = plan.smem;
     a.nbuf = 0; a.row_off = 0; a.row_stride = 0;
     {
         static int want_tma = -1;
@@ -795,12 +790,12 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
         // keep two CTAs per SM where the plan counted on them
         const size_t cap = (plan.smem <= 110 * 1024) ? (size_t)113 * 1024 : (size_t)kFusedMaxDynSmem;
         if (want_tma && !pairs_in && (row % 16) == 0 && (reinterpret_cast<uintptr_t>(lp) % 16) == 0 && row <= 32 * 1024 &&
-            plan.smem + extra + 4 * stride <= cap) {
-            const int nb = (int)((cap - plan.smem - extra) / stride);
+            plan.smem + 4 * stride <= cap) {
+            const int nb = (int)((cap - plan.smem) / stride);
             a.nbuf = nb < kMaxRowBufs ? nb : kMaxRowBufs;
-            a.row_off = (int)(plan.smem + extra);
+            a.row_off = (int)(plan.smem);
             a.row_stride = (int)stride;
-            smem = plan.smem + extra + (size_t)a.nbuf * stride;
+            smem = plan.smem + (size_t)a.nbuf * stride;
         }
     }
     {
