@@ -357,7 +357,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     if (tid == 0) { s_next = 0; s_bad = ok ? 0 : 1; }
     if (tid < kMaxChunks) s_flag[tid] = 0;
     if (tid < A.nbuf) mbar_init((uint32_t)__cvta_generic_to_shared(&s_bar[tid]), 1);
-    if (A.nbuf > 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (A.nbuf > 0) {                                   // make the initialised barriers visible to the async proxy (TMA)
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     if (MODE == 0 && A.tma_fill) {
         for (int k = tid; k < kZeroBytes / 4; k += kFusedThreads) zbuf[k] = 0.0f;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros -> async-proxy reads
