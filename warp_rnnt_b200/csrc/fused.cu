@@ -2,25 +2,29 @@
 // ((T+U)*U <~ 9k cells: BASELINE configs 1-3).  One launch does everything the reference spreads
 // over zeros_like + 4 kernels (+ python gather / mul_):
 //
-//   phase 0  gather      14 warps stage the lattice's blank/label log-probs into shared memory in
+//   phase 0  gather      up to 14 warps stage the lattice's blank/label log-probs into shared memory in
 //                        DIAGONAL-MAJOR, target-indexed form (replaces the python-level gather,
-//                        __init__.py:118-128, and the strided loads inside kernel_warp, core.cu:115-120).
-//                        Rows are staged from both ends towards the middle in 128-cell chunks, each
-//                        published with a release flag, so the two wavefronts START WHILE THE GATHER IS
-//                        STILL RUNNING and chase it (alpha needs the top rows first, beta the bottom rows)
+//                        __init__.py:118-128, and the strided loads inside kernel_warp, core.cu:115-120):
+//                        one TMA bulk copy per lattice row (U*V contiguous floats) into the warp's row
+//                        buffer, then two LDS per cell pick blank and label (fallback: LDG picks in
+//                        128-cell chunks).  Rows are staged from both ends towards the middle and each
+//                        warp publishes its progress (st.release), so the two wavefronts START WHILE THE
+//                        GATHER IS STILL RUNNING and chase it (alpha needs the top rows first, beta the
+//                        bottom rows)
 //   phase 1  wavefront   ONE warp runs alpha and one runs beta: lane l owns C adjacent lattice columns,
-//                        every anti-diagonal is one step = one __shfl_up + C independent LSE chains,
+//                        every anti-diagonal is one step = one shuffle + C independent LSE chains,
 //                        operands and results move as C-wide vector LDS/STS (conflict-free, because a
 //                        diagonal's cells are contiguous in the staged layout).  No inter-warp hand-off,
 //                        no barrier, no atomics on the recurrence (replaces kernel_warp + the
 //                        global-memory counts scheduler, core.cu:41-258)
-//            zero-fill   meanwhile the other 14 warps stream zeros over this CTA's slice of the dense
-//                        gradient with 256-bit evict_last stores (replaces at::zeros_like, binding.cpp:58);
-//                        the wavefront warps join through a shared work counter when they finish
+//            zero-fill   when the gather is done, the gather warps' lane 0 issue TMA bulk stores of a
+//                        zeroed shared-memory buffer (evict_last) over this CTA's slice of the dense
+//                        gradient (replaces at::zeros_like, binding.cpp:58); fallback: 256-bit stores
 //   phase 2  cost/guard  kernel_fill_costs (core.cu:334-370)
 //            patch       the <= 2 non-zeros per row are written into the freshly zeroed, still L2-resident
 //                        lines (kernel_grads_blank/label, core.cu:260-332), or -- MODE 1 -- the gradients
-//                        are emitted in (N,T,U,2) form for the deferred dense backward.
+//                        are emitted in (N,T,U,2) form for the deferred dense backward (+ loc for the
+//                        compact layout, whose lattices are addressed through mem_pref / lab_pref).
 //
 // grid (S, N): S CTAs per lattice recompute the (cheap) wavefront redundantly and split the
 // (bandwidth-bound) fill/patch of the lattice's rows, so small batches still use every SM.
@@ -37,8 +41,8 @@ constexpr float kBigF = -1.0e30f;   // finite stand-in for -inf (see wavefront.c
 // L2 residency control (B200: 126 MB L2).  The dense gradient slab is zero-filled while the
 // wavefront runs and patched afterwards; the patch is a partial-sector write, so it must still HIT
 // in L2 or ECC forces a DRAM read-modify-write per touched sector.  Filled lines are therefore
-// stored evict_last (256-bit STG.E.ELL2.256), and the one-pass log-prob gather is loaded
-// evict_first so that it cannot displace them.
+// stored evict_last (TMA bulk stores with an evict_last policy, or 256-bit STG.E.ELL2.256), and the
+// one-pass log-prob gather is loaded evict_first so that it cannot displace them.
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
