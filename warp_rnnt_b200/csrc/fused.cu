@@ -280,10 +280,13 @@ __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t ou
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             const float left = shfl_up1_ordered(val[C - 1]);   // lane 0 gets its own value: wl = kBig there
-            float nv[C];
-            nv[0] = lse<KIND>(val[0] + b[k][0], left + l[k][0]);
+            float nv[C], xs[C], ys[C];
 #pragma unroll
-            for (int c = 1; c < C; ++c) nv[c] = lse<KIND>(val[c] + b[k][c], val[c - 1] + l[k][c]);
+            for (int c = 0; c < C; ++c) {
+                xs[c] = val[c] + b[k][c];                             // row edge
+                ys[c] = (c == 0 ? left : val[c > 0 ? c - 1 : 0]) + l[k][c];   // column edge
+            }
+            lse_vec<KIND, C>(xs, ys, nv);
             if (KIND != kFast) {
                 const int i = d0 + k - first_col;              // row of the first real column on this diagonal
                 const uint32_t in = ((i >= 1) && (i < pre_rows)) ? 0xffffffffu : 0u;
