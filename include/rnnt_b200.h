@@ -72,6 +72,12 @@ uint64_t rnnt_b200_launch_count(void);
  * done, 7 kernel end (8..15 reserved).  `buf` is device memory, 16 * CTAs int64, zeroed by the caller.  NULL = off. */
 void rnnt_b200_debug_fused_trace(void *buf);
 
+/* Diagnostics (tests only): add `delta` to the alpha-side log-likelihood of sample `n` right before the
+ * forward/backward mismatch guard (core.cu:346-367) compares it with beta[0,0], so that the guard's FIRED branch
+ * (warning, zeroed gradient slab, cost = -(a+b)/2) can be exercised on well-formed input.  n < 0 = off (default).
+ * Process-wide; affects the dense and gathered layouts (the compact reference has no guard). */
+void rnnt_b200_debug_guard_poison(int n, float delta);
+
 /* ------------------------------------------------------------------------------------------
  * (A) native interface
  * ------------------------------------------------------------------------------------------ */

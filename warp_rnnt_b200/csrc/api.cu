@@ -17,6 +17,10 @@ namespace rnnt {
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static std::atomic<int> g_poison_n{-1};
+static std::atomic<float> g_poison_delta{0.0f};
+GuardPoison guard_poison() { return {g_poison_n.load(std::memory_order_relaxed), g_poison_delta.load(std::memory_order_relaxed)}; }
+
 static int env_lse_mode() {
     const char *e = getenv("RNNT_B200_LSE");
     if (!e) return RNNT_LSE_AUTO;
@@ -50,13 +54,15 @@ static int resolve_kind(int lse_mode, bool compact) {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // RNNT_B200_PATH = auto | fused | general  (tests exercise both paths on the same inputs)
-static int g_path = -1;
-static bool want_fused(int N, int T, int U, FusedPlan *plan) {
-    if (g_path < 0) {
+static int forced_path() {
+    static const int path = [] {
         const char *e = getenv("RNNT_B200_PATH");
-        g_path = (e && !strcmp(e, "general")) ? 2 : (e && !strcmp(e, "diag")) ? 4 : (e && !strcmp(e, "fused")) ? 1 : 0;
-    }
-    if (g_path >= 2) return false;
+        return (e && !strcmp(e, "general")) ? 2 : (e && !strcmp(e, "fused")) ? 1 : 0;
+    }();
+    return path;
+}
+static bool want_fused(int N, int T, int U, FusedPlan *plan) {
+    if (forced_path() >= 2) return false;
     return fused_plan(N, T, U, plan);
 }
 
@@ -98,61 +104,6 @@ static bool dense_args_ok(int N, int T, int U, int V) {
     return true;
 }
 
-// RNNT_B200_PATH=diag selects the diagonal-major general path (diag.cu) for every shape it supports.
-// It is verified by the same tests (bit-identical in exact mode) but NOT the default: measured on
-// B200 at cfg 4 it is slower end to end than the row-major path (3.28 ms vs 2.50 ms) -- its
-// single-warp wavefront is 1.6x faster (535 vs 836 us) but the scattered staging writes of
-// k_diag_gather / k_diag_grads cost more than that.  See DESIGN.md section 8.
-static bool want_diag(int N, int t_max, int u_max, DiagPlan *plan) {
-    if (g_path < 0) { FusedPlan f; (void)want_fused(1, 1, 1, &f); }
-    if (g_path != 4) return false;
-    return diag_plan(N, t_max, u_max, plan);
-}
-
-// Diagonal-major general path.  Scratch comes from the stream-ordered allocator (its size depends
-// on T and U, which rnnt_b200_workspace_bytes(cells, N) cannot see).  pg_out: (cells,2) gradients
-// or nullptr (costs only); when dense_out != nullptr the gradients are expanded to (cells,V).
-static int run_diag(cudaStream_t s, int kind, const Problem &p, const DiagPlan &plan, const float *lp,
-                    const int *labels, int V, int blank, int pairs_in, int64_t *loc, float *costs, float2 *pg_out,
-                    float *dense_out, const float *scale, int64_t cells, float lam, int guard) {
-    const size_t llb = align_up(sizeof(float) * 2 * p.N, 256), badb = align_up(sizeof(int) * p.N, 256);
-    const size_t pgb = (dense_out && !pg_out) ? align_up(sizeof(float2) * (size_t)cells, 256) : 0;
-    {
-        // keep freed scratch in the stream-ordered pool instead of returning it to the OS at every
-        // synchronisation (the default release threshold is 0, which makes each call re-map ~1 GB)
-        static bool pool_ready = false;
-        if (!pool_ready) {
-            int dev = 0;
-            cudaMemPool_t pool;
-            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                uint64_t thr = UINT64_MAX;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-            }
-            pool_ready = true;
-        }
-    }
-    char *tmp = nullptr;
-    if (cudaMallocAsync((void **)&tmp, align_up(plan.scratch_bytes, 256) + llb + badb + pgb, s) != cudaSuccess) {
-        cudaGetLastError();
-        return RNNT_STATUS_WORKSPACE_TOO_SMALL;
-    }
-    float *ll = (float *)(tmp + align_up(plan.scratch_bytes, 256));
-    int *bad = (int *)((char *)ll + llb);
-    float2 *pg = pg_out ? pg_out : (dense_out ? (float2 *)((char *)bad + badb) : nullptr);
-    int status = RNNT_STATUS_SUCCESS;
-    if (launch_diag_forward(s, kind, p, plan, tmp, lp, labels, V, blank, pairs_in, loc, ll, guard ? bad : nullptr, costs,
-                            pg, lam, guard) != cudaSuccess)
-        status = RNNT_STATUS_WARP_FAILED;
-    if (!status && dense_out) {
-        ExpandSrc src = {};
-        src.pg = pg; src.scale = scale; src.labels = labels; src.label_adds = 0;
-        Problem pd = p;
-        if (launch_expand(s, pd, src, dense_out, cells, V, blank) != cudaSuccess) status = RNNT_STATUS_GRADS_BLANK_FAILED;
-    }
-    cudaFreeAsync(tmp, s);
-    return status;
-}
-
 // Internal streams for the pipelined general path: one for gathers, one for emits, four
 // high-priority ones for wavefronts (their CTAs are few and long-lived; priority lets them take the
 // SMs that free up at every gather / emit kernel boundary).  Created once per process and device.
@@ -163,23 +114,21 @@ struct Pipeline {
     int device;
 };
 static bool pipeline_enabled() {
-    static int on = -1;
-    if (on < 0) {
-        // on by default (RNNT_B200_PIPELINE=0 disables).  Measured on B200, same box: cfg 5 micro-batch
-        // 2.23 ms pipelined vs 2.38 ms serial, cfg 4 2.85 vs 2.94 ms.  It only pays off with the
-        // early-retiring emit grid (launch_expand retire_early): persistent emit CTAs hold every SM
-        // until their kernel ends and the high-priority wavefront CTAs never get in (2.96 vs 2.90 ms).
-        const char *e = getenv("RNNT_B200_PIPELINE");
-        on = (e && !strcmp(e, "0")) ? 0 : 1;
-    }
-    return on == 1;
+    // on by default (RNNT_B200_PIPELINE=0 disables).  Measured on B200, same box: cfg 5 micro-batch
+    // 2.23 ms pipelined vs 2.38 ms serial, cfg 4 2.85 vs 2.94 ms.  It only pays off with the
+    // early-retiring emit grid (launch_expand retire_early): persistent emit CTAs hold every SM
+    // until their kernel ends and the high-priority wavefront CTAs never get in (2.96 vs 2.90 ms).
+    static const bool on = !env_is("RNNT_B200_PIPELINE", '0');
+    return on;
 }
-static Pipeline *get_pipeline() {
-    static Pipeline *pl = nullptr;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    if (pl && pl->device == dev) return pl;
-    if (pl) return nullptr;                      // a second device in one process: keep it simple, no pipeline
+// One pipeline per device (streams and events belong to a device); created on first use under g_pipe_mu,
+// which also serialises the calls that use a pipeline's shared events.
+static std::mutex g_pipe_mu;
+static Pipeline *get_pipeline_locked() {
+    static Pipeline *pipes[kMaxDevices] = {};
+    const int dev = current_device();
+    if (dev >= kMaxDevices) return nullptr;
+    if (pipes[dev]) return pipes[dev];
     Pipeline *p = new Pipeline();
     p->device = dev;
     int lo = 0, hi = 0;
@@ -195,8 +144,8 @@ static Pipeline *get_pipeline() {
     for (int i = 0; i < 2 + Pipeline::kWave && ok; ++i)
         ok = cudaEventCreateWithFlags(&p->join[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { cudaGetLastError(); delete p; return nullptr; }
-    pl = p;
-    return pl;
+    pipes[dev] = p;
+    return p;
 }
 
 #define RNNT_TRY(expr, code)                                            \
@@ -237,6 +186,10 @@ void rnnt_b200_set_lse_mode(int mode) {
 int rnnt_b200_get_lse_mode(void) { return default_lse_mode(); }
 
 uint64_t rnnt_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void rnnt_b200_debug_guard_poison(int n, float delta) {
+    g_poison_delta.store(delta, std::memory_order_relaxed);
+    g_poison_n.store(n, std::memory_order_relaxed);
+}
 void rnnt_b200_debug_fused_trace(void *buf) { rnnt::set_fused_trace(static_cast<long long *>(buf)); }
 
 size_t rnnt_b200_workspace_bytes(int64_t cells, int N) { return carve(nullptr, cells, N).bytes; }
@@ -256,12 +209,6 @@ int rnnt_b200_loss_dense(void *stream, void *workspace, size_t workspace_bytes, 
                  RNNT_STATUS_WARP_FAILED);
         return RNNT_STATUS_SUCCESS;
     }
-    DiagPlan dplan;
-    if (want_diag(N, T, U, &dplan)) {
-        Problem pd = {xn, yn, nullptr, nullptr, N, T, U, 0};
-        return run_diag(s, resolve_kind(lse_mode, false), pd, dplan, log_probs, labels, V, blank, 0, nullptr, costs,
-                        nullptr, grads, grad_scale, cells, fastemit_lambda, 1);
-    }
     const Workspace w = carve(workspace, cells, N);
     if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
     const int kind = resolve_kind(lse_mode, false);
@@ -270,10 +217,9 @@ int rnnt_b200_loss_dense(void *stream, void *workspace, size_t workspace_bytes, 
     const int groups = (grads && N >= 8 && (int64_t)cells * V * 4 >= ((int64_t)512 << 20) && pipeline_enabled())
                            ? (N >= 32 ? 8 : 4) : 1;
     if (groups > 1) {
-        Pipeline *pl = get_pipeline();
+        std::lock_guard<std::mutex> lock(g_pipe_mu);    // the pipeline's events are shared by all calls on this device
+        Pipeline *pl = get_pipeline_locked();
         if (pl) {
-            static std::mutex mu;                   // the internal events are shared by all calls
-            std::lock_guard<std::mutex> lock(mu);
             int status = RNNT_STATUS_SUCCESS;
             cudaEventRecord(pl->fork, s);
             cudaStreamWaitEvent(pl->gather_s, pl->fork, 0);
@@ -341,12 +287,6 @@ int rnnt_b200_loss_pairs(void *stream, void *workspace, size_t workspace_bytes, 
                  RNNT_STATUS_WARP_FAILED);
         return RNNT_STATUS_SUCCESS;
     }
-    DiagPlan dplan;
-    if (want_diag(N, T, U, &dplan)) {
-        Problem pd = {xn, yn, nullptr, nullptr, N, T, U, 0};
-        return run_diag(s, resolve_kind(lse_mode, false), pd, dplan, pairs, nullptr, 2, 0, 1, nullptr, costs,
-                        reinterpret_cast<float2 *>(pair_grads), nullptr, nullptr, cells, fastemit_lambda, 1);
-    }
     const Workspace w = carve(workspace, cells, N);
     if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
     Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
@@ -375,12 +315,6 @@ int rnnt_b200_gather_forward(void *stream, void *workspace, size_t workspace_byt
                               reinterpret_cast<float2 *>(pair_grads), nullptr, N, T, U, V, blank, fastemit_lambda, 0, 1),
                  RNNT_STATUS_WARP_FAILED);
         return RNNT_STATUS_SUCCESS;
-    }
-    DiagPlan dplan;
-    if (want_diag(N, T, U, &dplan)) {
-        Problem pd = {xn, yn, nullptr, nullptr, N, T, U, 0};
-        return run_diag(s, resolve_kind(lse_mode, false), pd, dplan, log_probs, labels, V, blank, 0, nullptr, costs,
-                        reinterpret_cast<float2 *>(pair_grads), nullptr, nullptr, cells, fastemit_lambda, 1);
     }
     const Workspace w = carve(workspace, cells, N);
     if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
@@ -433,12 +367,6 @@ int rnnt_b200_compact_forward(void *stream, void *workspace, size_t workspace_by
                               fastemit_lambda, 0, 0, w.mem_pref, w.lab_pref, loc),
                  RNNT_STATUS_WARP_FAILED);
         return RNNT_STATUS_SUCCESS;
-    }
-    DiagPlan dplan;
-    if (max_T > 0 && max_U > 0 && want_diag(N, max_T, max_U, &dplan)) {
-        // no mismatch guard in the compact reference (core_compact.cu:347-358)
-        return run_diag(s, resolve_kind(lse_mode, true), p, dplan, xs, ys, V, blank, 0, loc, costs,
-                        reinterpret_cast<float2 *>(pair_grads), nullptr, nullptr, STU, fastemit_lambda, 0);
     }
     RNNT_TRY(launch_gather(s, p, xs, ys, V, blank, w.pairs, loc, STU), RNNT_STATUS_GATHER_FAILED);
     // no mismatch guard in the compact reference (core_compact.cu:347-358)

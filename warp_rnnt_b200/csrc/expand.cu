@@ -170,9 +170,7 @@ cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src
     int rows = (int)(65536 / ((int64_t)V * 4));
     rows = max(1, min(rows, kExpandMaxRows));
     const int64_t nchunks = (cells + rows - 1) / rows;
-    int sms = 148;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count(current_device());
     // persistent CTAs by default; retire_early = one CTA per few chunks, so that SM resources keep freeing
     // up for the high-priority wavefront CTAs of the pipelined path
     const int64_t cap = retire_early ? (int64_t)sms * 64 : (int64_t)sms * 8;

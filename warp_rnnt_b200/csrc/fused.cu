@@ -196,6 +196,8 @@ struct FusedArgs {
     int gw;                 // warps that gather (of the 14 non-wavefront warps); MODE 0: the rest start the zero-fill at once
     int tma_fill;           // MODE 0: zero-fill with bulk shared->global copies (else 256-bit STG)
     long long *trace;       // optional per-CTA phase stamps (clock64), 8 per CTA; null = off
+    int poison_n;           // test hook: sample whose alpha-side ll gets poison_delta added before the guard (-1 = off)
+    float poison_delta;
 };
 
 // One direction of one lattice, one warp.  Diagonal-major, target-indexed operands:
@@ -586,7 +588,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         if (ok) {
             float b = BE[idxB(0, 0)];                   // beta[0,0]
             if (A.guard) {
-                const float a = AL[idxA(T1, U1)] + WBb[idxB(T1, U1)];   // alpha-side ll (core.cu:346)
+                float a = AL[idxA(T1, U1)] + WBb[idxB(T1, U1)];   // alpha-side ll (core.cu:346)
+                if (n == A.poison_n) a += A.poison_delta;              // test hook, see rnnt_b200_debug_guard_poison
                 const float ratio = fabsf(a - b) / fabsf(fmaxf(a, b));
                 if (ratio > 0.001f) {
                     if (slice == 0)
@@ -718,8 +721,7 @@ bool fused_plan(int N, int T, int U, FusedPlan *plan) {
     const size_t smem = fused_smem_bytes(T, U, Wd, nd);
     if (smem > 220 * 1024) return false;
     if (((int64_t)T * U + kChunkCells - 1) / kChunkCells > kMaxChunks) return false;
-    int sms = 148, dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count(current_device());
     // CTAs per lattice: fill every SM (two CTAs per SM when two staged lattices fit in its shared memory)
     const int per_sm = (smem <= 110 * 1024) ? 2 : 1;
     int slices = (per_sm * sms) / N;
@@ -730,24 +732,31 @@ bool fused_plan(int N, int T, int U, FusedPlan *plan) {
 
 template <int KIND, int MODE, int C>
 static cudaError_t launch_fused_kmc(cudaStream_t s, FusedArgs a, size_t smem) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_fused<KIND, MODE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedMaxDynSmem);
+    static std::atomic<bool> attr_done[kMaxDevices];
+    {
+        const cudaError_t e = ensure_dyn_smem(k_fused<KIND, MODE, C>, attr_done, kFusedMaxDynSmem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     if (a.slices > 1) {
         // CTAs per lattice: fill every SM with what is actually co-resident (registers can forbid the second
-        // CTA that shared memory would allow; a second, partial wave costs more than it brings)
-        static size_t occ_smem = ~(size_t)0;
-        static int occ = 1, sms = 148;
-        if (occ_smem != smem) {
-            int dev = 0, n = 1;
-            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fused<KIND, MODE, C>, kFusedThreads, smem) == cudaSuccess && n >= 1) occ = n;
-            occ_smem = smem;
+        // CTA that shared memory would allow; a second, partial wave costs more than it brings).  Cached per device.
+        struct Occ { size_t smem = ~(size_t)0; int occ = 1; };
+        static Occ cache[kMaxDevices];
+        static std::mutex mu;
+        const int dev = current_device();
+        int occ = 1;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            Occ local;
+            Occ &o = dev < kMaxDevices ? cache[dev] : local;
+            if (o.smem != smem) {
+                int n = 1;
+                o.occ = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fused<KIND, MODE, C>, kFusedThreads, smem) == cudaSuccess && n >= 1) ? n : 1;
+                o.smem = smem;
+            }
+            occ = o.occ;
         }
-        a.slices = max(1, min(a.slices, (occ * sms) / a.N));
+        a.slices = max(1, min(a.slices, (occ * sm_count(dev)) / a.N));
     }
     dim3 grid(a.slices, a.N);
     k_fused<KIND, MODE, C><<<grid, kFusedThreads, smem, s>>>(a);
@@ -775,12 +784,8 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
     a.scale = scale; a.N = N; a.T = T; a.U = U; a.V = V; a.blank = blank; a.lam = lam; a.pairs_in = pairs_in;
     a.guard = guard; a.slices = (grads || pair_grads) ? plan.slices : 1; a.Wd = plan.W; a.nd = plan.ring;
     {
-        static int gw_env = -1;                         // tuning knob: RNNT_B200_GATHER_WARPS in [2,16]
-        if (gw_env < 0) {
-            const char *e = getenv("RNNT_B200_GATHER_WARPS");
-            gw_env = e ? atoi(e) : 0;
-            if (gw_env < 1 || gw_env > kFusedThreads / 32 - 2) gw_env = 0;
-        }
+        static const int gw_raw = env_int("RNNT_B200_GATHER_WARPS", 0);   // tuning knob, in [1,14]
+        const int gw_env = (gw_raw < 1 || gw_raw > kFusedThreads / 32 - 2) ? 0 : gw_raw;
         // fast LSE: the fill (HBM-write bound) outlasts the wavefront, so start it during the gather;
         // exact LSE: the wavefront outlasts the fill, so let every free warp gather and feed it sooner
         // (measured with the TMA fill: starting the fill only when the gather is done is best in both modes)
@@ -793,8 +798,7 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
     size_t smem = plan.smem;
     a.nbuf = 0; a.row_off = 0; a.row_stride = 0;
     {
-        static int want_tma = -1;
-        if (want_tma < 0) { const char *e = getenv("RNNT_B200_GATHER"); want_tma = (e && e[0] == 'l') ? 0 : 1; }
+        static const bool want_tma = !env_is("RNNT_B200_GATHER", 'l');
         const size_t row = (size_t)U * V * sizeof(float);
         const size_t stride = (row + 127) / 128 * 128;
         // keep two CTAs per SM where the plan counted on them
@@ -809,11 +813,11 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
         }
     }
     {
-        static int tma = -1;                            // RNNT_B200_FILL=stg selects the 256-bit store fill
-        if (tma < 0) { const char *e = getenv("RNNT_B200_FILL"); tma = (e && e[0] == 's') ? 0 : 1; }
-        a.tma_fill = tma;
+        static const bool tma = !env_is("RNNT_B200_FILL", 's');   // RNNT_B200_FILL=stg selects the 256-bit store fill
+        a.tma_fill = tma ? 1 : 0;
     }
     a.trace = g_fused_trace;
+    { const GuardPoison gp = guard_poison(); a.poison_n = gp.n; a.poison_delta = gp.delta; }
     const bool dense = grads != nullptr;
     const int C = plan.nw;
     if (kind == kFast)

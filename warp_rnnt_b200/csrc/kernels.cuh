@@ -5,6 +5,10 @@
 namespace rnnt {
 
 void count_launch();   // api.cu: bumps the library-wide launch counter
+// api.cu: test hook (rnnt_b200_debug_guard_poison): sample index whose alpha-side log-likelihood gets `delta` added
+// in front of the forward/backward mismatch guard; n < 0 = off
+struct GuardPoison { int n; float delta; };
+GuardPoison guard_poison();
 
 cudaError_t launch_prefix(cudaStream_t s, const int *xn, const int *yn, int N, int64_t *mem_pref,
                           int64_t *lab_pref, int *totals);
@@ -45,12 +49,5 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
                          const float *scale, int N, int T, int U, int V, int blank, float lam, int pairs_in,
                          int guard, const int64_t *mem_pref = nullptr, const int64_t *lab_pref = nullptr,
                          int64_t *loc = nullptr);   // mem_pref != null: compact layout, T/U = max lengths
-
-// diag.cu -- general path on diagonal-major staged operands (any T, U <= 512)
-struct DiagPlan { int C, Wd, nd, t_cap; size_t smem; int64_t plane; size_t scratch_bytes; };
-bool diag_plan(int N, int t_max, int u_max, DiagPlan *plan);
-cudaError_t launch_diag_forward(cudaStream_t s, int kind, const Problem &p, const DiagPlan &plan, void *scratch,
-                                const float *lp, const int *labels, int V, int blank, int pairs_in, int64_t *loc,
-                                float *ws_ll, int *bad, float *costs, float2 *pg, float fastemit_lambda, int guard);
 
 }  // namespace rnnt

@@ -400,7 +400,8 @@ template <int KIND>
 __global__ void __launch_bounds__(512, 1) k_wavefront(Problem p, const float2 *__restrict__ pairs,
                                                     float *__restrict__ alphas, float *__restrict__ betas,
                                                     float *__restrict__ ws_ll, int *__restrict__ bad,
-                                                    float *__restrict__ costs, int beta_only, int guard, int ring_size) {
+                                                    float *__restrict__ costs, int beta_only, int guard, int ring_size,
+                                                    GuardPoison poison) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nwarps = blockDim.x >> 5;
     Slot *ring = reinterpret_cast<Slot *>(smem_raw);
@@ -428,7 +429,8 @@ __global__ void __launch_bounds__(512, 1) k_wavefront(Problem p, const float2 *_
             float b = __ldcg(ws_ll + p.N + n);
             if (!beta_only && guard) {
                 // forward/backward mismatch guard, core.cu:346-367
-                const float a = __ldcg(ws_ll + n);
+                float a = __ldcg(ws_ll + n);
+                if (n == poison.n) a += poison.delta;      // test hook, see rnnt_b200_debug_guard_poison
                 const float ratio = fabsf(a - b) / fabsf(fmaxf(a, b));
                 if (ratio > 0.001f) {
                     printf("\nWARNING: sample %d [%d, %d] has a forward/backward mismatch %f / %f\n", n, L.Tn,
@@ -532,11 +534,10 @@ static cudaError_t launch_wavefront_kind(cudaStream_t s, const Problem &p, const
         while (ring < t_hint && (size_t)ring * 2 * nwarps * sizeof(Slot) <= 160 * 1024) ring *= 2;
     }
     const size_t smem = sizeof(Slot) * (size_t)nwarps * ring + sizeof(int) * nwarps;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_wavefront<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    static std::atomic<bool> attr_done[kMaxDevices];
+    {
+        const cudaError_t e = ensure_dyn_smem(k_wavefront<KIND>, attr_done, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(beta_only ? 1 : 2, p.N, 1);
@@ -552,7 +553,7 @@ static cudaError_t launch_wavefront_kind(cudaStream_t s, const Problem &p, const
     cfg.numAttrs = 1;
     count_launch();
     return cudaLaunchKernelEx(&cfg, k_wavefront<KIND>, p, pairs, alphas, betas, ws_ll, bad, costs, beta_only, guard,
-                              ring);
+                              ring, guard_poison());
 }
 
 cudaError_t launch_wavefront(cudaStream_t s, int kind, const Problem &p, const float2 *pairs, float *alphas,
