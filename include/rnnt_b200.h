@@ -97,6 +97,28 @@ int rnnt_b200_loss_dense(void *stream, void *workspace, size_t workspace_bytes,
                          float *costs, float *grads, const float *grad_scale,
                          int N, int T, int U, int V, int blank, float fastemit_lambda, int lse_mode);
 
+/* rnnt_b200_loss_dense plus the reduction of the python API (__init__.py:132-143) fused in:
+ *   loss_sum (1) f32 out or NULL: sum_n costs[n] * (grad_scale ? grad_scale[n] : 1), summed in a fixed order
+ *     (deterministic; lane-strided partials + shuffle tree, so the low bits differ from torch.sum's order).
+ *     With grad_scale[n] = 1/N ('mean'), 1/xn[n] (average_frames) or their product this is the reduced loss and
+ *     `grads` is already d loss / d log_probs -- one launch for what the reference does in
+ *     zeros_like + 4 kernels + sum/mean + mul_.
+ *   sync_counter: one device `unsigned`, 0 on entry, left at 0 on exit (self-resetting ticket for the
+ *     last-CTA reduction of the single-kernel path; one counter per concurrently running call).  NULL: the
+ *     reduction runs as a second tiny launch instead. */
+int rnnt_b200_loss_dense_reduced(void *stream, void *workspace, size_t workspace_bytes,
+                                 const float *log_probs, const int *labels, const int *xn, const int *yn,
+                                 float *costs, float *grads, const float *grad_scale, float *loss_sum,
+                                 unsigned int *sync_counter, int N, int T, int U, int V, int blank,
+                                 float fastemit_lambda, int lse_mode);
+
+/* In-place grads[n, :] *= grad_out[n * grad_out_stride] / (applied ? applied[n] : 1) for the samples where the two
+ * differ (stride 0: one upstream scalar for all samples).  Replaces RNNTLoss.backward's dense mul_
+ * (__init__.py:21-24): when the upstream gradient equals what the forward already multiplied in (the usual
+ * loss.backward()), no memory is touched.  With applied == NULL the product is exactly the reference's. */
+int rnnt_b200_rescale(void *stream, float *grads, const float *grad_out, int grad_out_stride,
+                      const float *applied, int N, int64_t elems_per_sample);
+
 /* Gathered layout (N,T,U,2) = [blank, label] per cell.  Replaces run_warp_rnnt_gather
  * (core.h:35-39).  pair_grads (N,T,U,2) out, fully written (zeros on padding); NULL = fwd only. */
 int rnnt_b200_loss_pairs(void *stream, void *workspace, size_t workspace_bytes,

@@ -197,7 +197,8 @@ def test_compact_shape_errors(w):
 
 # ------------------------------------------------------------------ python API / autograd
 @pytest.mark.parametrize("gather", [False, True])
-@pytest.mark.parametrize("reduction,avg", [("none", False), ("mean", True), ("sum", False)])
+@pytest.mark.parametrize("reduction,avg", [("none", False), ("mean", True), ("sum", False), ("none", True),
+                                           ("sum", True), ("mean", False), (None, False)])
 def test_python_api_autograd(w, gather, reduction, avg):
     N, T, U, V = 4, 21, 13, 9
     lp, ys, xn, yn = make_inputs(N, T, U, V, seed=3, random_lengths=True, blank=0)
@@ -206,7 +207,7 @@ def test_python_api_autograd(w, gather, reduction, avg):
     loss = w.rnnt_loss(x, cu(ys), cu(xn), cu(yn), average_frames=avg, reduction=reduction, gather=gather,
                        fastemit_lambda=0.1)
     go = np.linspace(1.0, 2.0, N)
-    if reduction == "none":
+    if reduction in ("none", None):
         (loss * cu(go.astype(np.float32))).sum().backward()
         loss0, g0 = oracle.rnnt_loss(lp, ys, xn, yn, avg, reduction, 0, gather, 0.1, grad_output=go)
     else:
@@ -214,6 +215,42 @@ def test_python_api_autograd(w, gather, reduction, avg):
         loss0, g0 = oracle.rnnt_loss(lp, ys, xn, yn, avg, reduction, 0, gather, 0.1)
     np.testing.assert_allclose(loss.detach().cpu().numpy(), loss0, rtol=1e-5)
     np.testing.assert_allclose(x.grad.cpu().numpy(), g0, atol=2 * gtol(T, U))
+
+
+def test_python_api_one_launch_and_upstream_scaling(w):
+    """rnnt_loss(reduction=...) + backward on the dense path: ONE fused kernel produces costs, the reduced loss and the
+    final gradient; backward adds only the rescale check (which rescales when the upstream gradient is not 1)."""
+    N, T, U, V = 5, 33, 17, 11
+    lp, ys, xn, yn = make_inputs(N, T, U, V, seed=12, random_lengths=True)
+    args = (cu(ys), cu(xn), cu(yn))
+    w.set_lse_mode("exact")
+    for reduction, avg in (("sum", False), ("mean", True)):
+        loss0, g0 = oracle.rnnt_loss(lp, ys, xn, yn, avg, reduction)
+        x = cu(lp).requires_grad_(True)
+        torch.cuda.synchronize()
+        n0 = w._C.launch_count()
+        loss = w.rnnt_loss(x, *args, average_frames=avg, reduction=reduction)
+        assert w._C.launch_count() - n0 == 1                       # k_fused: costs + loss + gradient
+        loss.backward()
+        assert w._C.launch_count() - n0 == 2                       # + k_rescale (returns at once: upstream == 1)
+        np.testing.assert_allclose(loss.item(), loss0, rtol=1e-6)
+        np.testing.assert_allclose(x.grad.cpu().numpy(), g0, atol=2 * gtol(T, U))
+        g1 = x.grad.clone()
+        # upstream gradient != 1: (3 * loss).backward() must give exactly 3 * the gradient above
+        x2 = cu(lp).requires_grad_(True)
+        (3.0 * w.rnnt_loss(x2, *args, average_frames=avg, reduction=reduction)).backward()
+        assert torch.equal(x2.grad, g1 * 3.0)
+        # reduced loss == reduction of the per-sample costs (fixed-order sum in the kernel vs torch's order)
+        costs = w.rnnt_loss(cu(lp), *args, average_frames=avg, reduction="none")
+        red = costs.sum() if reduction == "sum" else costs.mean()
+        np.testing.assert_allclose(loss.item(), red.item(), rtol=2e-6)
+    # a second backward through the same graph has no buffer left: clear error instead of a wrong gradient
+    x = cu(lp).requires_grad_(True)
+    loss = w.rnnt_loss(x, *args, reduction="sum")
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second time"):
+        loss.backward()
+    w.set_lse_mode("auto")
 
 
 def test_python_api_compact_autograd(w):

@@ -39,7 +39,7 @@ def _oracle_loss_fn(lp, ys, xn, yn, average_frames=False, reduction="none", blan
     costs = _OracleLoss.apply(lp, ys, xn, yn, fastemit_lambda)
     if average_frames:
         costs = costs / xn.to(costs)
-    return costs
+    return costs.sum() if reduction == "sum" else (costs.mean() if reduction == "mean" else costs)
 
 
 def _worker(rank, world, port, reduction, out):
@@ -56,7 +56,18 @@ def _worker(rank, world, port, reduction, out):
                                       fastemit_lambda=0.1, loss_fn=_oracle_loss_fn)
     loss.backward()
     lo, hi = parallel.shard_range(N, world, rank)
-    out.put((rank, float(loss), lo, hi, x.grad.numpy()))
+    # the same shard as micro-batches of <= 2 lattices, with the caller-known global batch size: one all-reduce
+    xs_mb = [sh[0][i:i + 2].clone().requires_grad_(True) for i in range(0, hi - lo, 2)]
+    batches = [(xm, sh[1][i:i + 2], sh[2][i:i + 2], sh[3][i:i + 2]) for xm, i in zip(xs_mb, range(0, hi - lo, 2))]
+    loss_mb = parallel.rnnt_loss_microbatches(batches, global_batch=N, reduction=reduction, average_frames=True,
+                                              fastemit_lambda=0.1, loss_fn=_oracle_loss_fn)
+    grad_mb = torch.cat([xm.grad for xm in xs_mb], 0).numpy()
+    # 'mean' with global_batch given: a 1-element all-reduce, same value
+    x2 = sh[0].clone().requires_grad_(True)
+    loss_gb = parallel.rnnt_loss_sharded(x2, sh[1], sh[2], sh[3], average_frames=True, reduction=reduction,
+                                         fastemit_lambda=0.1, loss_fn=_oracle_loss_fn, global_batch=N)
+    loss_gb.backward()
+    out.put((rank, float(loss), lo, hi, x.grad.numpy(), float(loss_mb), grad_mb, float(loss_gb), x2.grad.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -77,10 +88,14 @@ def test_sharded_loss_two_ranks(reduction):
     N, T, U, V = 5, 7, 4, 6
     lp, ys, xn, yn = make_inputs(N, T, U, V, seed=9, random_lengths=True)
     loss0, g0 = oracle.rnnt_loss(lp, ys, xn, yn, average_frames=True, reduction=reduction, fastemit_lambda=0.1)
-    for rank, loss, lo, hi, grad in res:
+    for rank, loss, lo, hi, grad, loss_mb, grad_mb, loss_gb, grad_gb in res:
         np.testing.assert_allclose(loss, loss0, rtol=1e-12)          # identical on every rank
         np.testing.assert_allclose(grad, g0[lo:hi], atol=1e-13)      # gradients stay rank-local
-    assert sorted((lo, hi) for _, _, lo, hi, _ in res) == [(0, 3), (3, 5)]
+        np.testing.assert_allclose(loss_mb, loss0, rtol=1e-12)       # micro-batched step == one-call step
+        np.testing.assert_allclose(grad_mb, g0[lo:hi], atol=1e-13)
+        np.testing.assert_allclose(loss_gb, loss0, rtol=1e-12)
+        np.testing.assert_allclose(grad_gb, g0[lo:hi], atol=1e-13)
+    assert sorted((r[2], r[3]) for r in res) == [(0, 3), (3, 5)]
 
 
 def test_shard_range_partitions():

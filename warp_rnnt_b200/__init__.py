@@ -12,10 +12,12 @@ Host code here is plumbing only (argument handling, autograd wiring); all arithm
 hand-written sm_100a kernels of ``lib/librnnt_b200.so`` through ``lib/_C.so``.  There is no CPU or
 eager-PyTorch fallback: importing this package without the built extension raises ImportError.
 """
+import contextlib
 import importlib.machinery
 import importlib.util
 import os
 import sys
+import threading
 
 import torch
 
@@ -57,42 +59,75 @@ def set_lse_mode(mode):
 
 
 class RNNTLoss(torch.autograd.Function):
-    """Dense / gathered-input loss.  Reference: ``RNNTLoss`` (__init__.py:9-24).
+    """Dense loss, ONE kernel launch per step.  Reference: ``RNNTLoss`` (__init__.py:9-24).
 
-    The reference materialises the dense gradient in forward and multiplies it in place by
-    grad_output in backward (two more dense passes).  Here forward keeps the gradient in its
-    (N,T,U,2) [blank,label] form and backward emits the dense (N,T,U,V) tensor once, already
-    scaled by grad_output -- one dense write in total.  With ``blank == -1`` the input is the
-    gathered (N,T,U,2) layout of the reference's operator boundary (binding.cpp:81-90)."""
+    Like the reference, forward produces the dense gradient; unlike it, the python-level reduction
+    (average_frames, 'sum' / 'mean', __init__.py:132-143) is part of this Function: the per-sample weights
+    ``weights[n]`` (1/N, 1/frames, ...) go into the kernel as ``grad_scale``, the kernel returns
+    ``sum_n weights[n] * cost[n]`` itself (``reduce=True``) and the gradient it wrote already is
+    d(loss)/d(log_probs).  Backward then only has to compare the upstream gradient with what was multiplied
+    in (``rnnt_rescale_``: a tiny launch that touches no gradient memory when they agree -- the usual
+    ``loss.backward()``) instead of the reference's dense ``mul_`` (two more passes over (N,T,U,V)).
+
+    With ``blank == -1`` the input is the gathered (N,T,U,2) layout of the reference's operator boundary
+    (binding.cpp:81-90); weights / reduce are not supported there."""
 
     @staticmethod
     def forward(ctx, log_probs, labels, frames_lengths, labels_lengths, blank=0, fastemit_lambda=0.0,
-                accumulate=False):
+                weights=None, reduce=False):
         need = ctx.needs_input_grad[0]
-        ctx.pairs_in = (blank == -1)
-        if ctx.pairs_in:
+        ctx.need = need
+        if blank == -1:
+            assert weights is None and not reduce
             costs, grads = _C.rnnt_loss_dense(log_probs, labels, frames_lengths, labels_lengths, -1,
                                               fastemit_lambda, None, need, 0)
             ctx.grads = grads if need else None
-        else:
-            costs, pg = _C.rnnt_gather_forward(log_probs, labels, frames_lengths, labels_lengths, blank,
-                                               fastemit_lambda, need, 0)
-            ctx.grads = pg if need else None
-            ctx.labels = labels
-            ctx.V = log_probs.size(3)
-            ctx.blank = blank
-            ctx.accumulate = accumulate
+            return costs
+        costs, grads, loss = _C.rnnt_loss_fused(log_probs, labels, frames_lengths, labels_lengths, blank,
+                                                fastemit_lambda, weights, need, 0)
+        ctx.grads = grads if need else None
+        if reduce:
+            return loss[0]
+        return costs if weights is None else costs * weights
+
+    @staticmethod
+    def backward(ctx, grads_output):
+        if not ctx.need:
+            return None, None, None, None, None, None, None, None
+        g, ctx.grads = ctx.grads, None       # hand the buffer over: autograd can then adopt it as .grad without a copy
+        if g is None:
+            raise RuntimeError("RNNTLoss: backward called a second time, but the gradient buffer produced by forward "
+                               "has already been handed to autograd (run forward again)")
+        go = grads_output.detach().reshape(-1).to(torch.float32).contiguous()
+        _C.rnnt_rescale_(g, go, None)        # in place, like the reference's mul_ (__init__.py:23); no-op when go == 1
+        return g, None, None, None, None, None, None, None
+
+
+class RNNTLossGather(torch.autograd.Function):
+    """``gather=True``: the reference's memory-saving mode (__init__.py:118-128).  Forward keeps the gradient in
+    its (N,T,U,2) [blank,label] form -- the log-prob gather runs inside the forward kernel, without the int64
+    index tensor -- and backward emits the dense (N,T,U,V) tensor once, already scaled by grad_output (replaces
+    mul_ + GatherBackward's zeros + scatter_add_).  A label equal to ``blank`` adds both gradients, as
+    torch.gather's backward does."""
+
+    @staticmethod
+    def forward(ctx, log_probs, labels, frames_lengths, labels_lengths, blank=0, fastemit_lambda=0.0):
+        need = ctx.needs_input_grad[0]
+        costs, pg = _C.rnnt_gather_forward(log_probs, labels, frames_lengths, labels_lengths, blank,
+                                           fastemit_lambda, need, 0)
+        ctx.grads = pg if need else None
+        ctx.labels = labels
+        ctx.V = log_probs.size(3)
+        ctx.blank = blank
         return costs
 
     @staticmethod
     def backward(ctx, grads_output):
         if ctx.grads is None:
-            return None, None, None, None, None, None, None
+            return None, None, None, None, None, None
         go = grads_output.contiguous().to(ctx.grads.dtype)
-        if ctx.pairs_in:
-            return ctx.grads * go.view(-1, 1, 1, 1), None, None, None, None, None, None
-        g = _C.rnnt_gather_backward(ctx.grads, ctx.labels, go, ctx.V, ctx.blank, ctx.accumulate)
-        return g, None, None, None, None, None, None
+        g = _C.rnnt_gather_backward(ctx.grads, ctx.labels, go, ctx.V, ctx.blank, True)
+        return g, None, None, None, None, None
 
 
 class RNNTLossEager(torch.autograd.Function):
@@ -111,15 +146,33 @@ class RNNTLossEager(torch.autograd.Function):
         return ctx.grads.mul_(grads_output), None, None, None, None, None
 
 
+_tls = threading.local()
+
+
+@contextlib.contextmanager
+def compact_hints(max_T, max_U):
+    """Inside this context ``rnnt_loss(compact=True)`` trusts the caller's upper bounds of ``frames_lengths`` and
+    ``labels_lengths + 1`` and skips the shape validation that needs a device->host copy of the length sums (the
+    reference does four ``.item()`` syncs there, binding.cpp:132-146): the forward then has no host sync at all
+    and can be captured into a CUDA graph.  A sample exceeding the bounds gets cost NaN."""
+    prev = getattr(_tls, "hints", None)
+    _tls.hints = (int(max_T), int(max_U))
+    try:
+        yield
+    finally:
+        _tls.hints = prev
+
+
 class RNNTLossCompact(torch.autograd.Function):
     """Compact (ragged) layout.  Reference: ``RNNTLossCompact`` (__init__.py:26-54)."""
 
     @staticmethod
     def forward(ctx, log_probs, labels, frames_lengths, labels_lengths, blank=0, fastemit_lambda=0.0,
                 enable_grad: bool = True):
+        hints = getattr(_tls, "hints", None) or (0, 0)
         costs, grads, loc = _C.rnnt_loss_compact(
             xs=log_probs, ys=labels, xn=frames_lengths, yn=labels_lengths, blank=blank,
-            fastemit_lambda=fastemit_lambda, required_grad=enable_grad)
+            fastemit_lambda=fastemit_lambda, required_grad=enable_grad, max_T=hints[0], max_U=hints[1])
         if enable_grad:
             cumlen = torch.cumsum(frames_lengths * (labels_lengths + 1), dim=0, dtype=torch.int32)
             ctx.V = log_probs.size(-1)
@@ -146,9 +199,10 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=
         average_frames: divide each sample's loss by its number of frames.
         reduction: 'none' | 'mean' | 'sum' | None.
         blank: blank label id.
-        gather: the reference's memory-saving mode.  Here both settings keep only a (N,T,U,2)
-            gradient between forward and backward; ``gather=True`` additionally follows
-            torch.gather's backward for a label equal to ``blank`` (the two gradients add).
+        gather: the reference's memory-saving mode: only a (N,T,U,2) gradient lives between forward and
+            backward (the dense one is emitted by backward); follows torch.gather's backward for a label
+            equal to ``blank`` (the two gradients add).  ``gather=False`` (default) is the fast path: one
+            kernel launch produces loss and dense gradient.
         fastemit_lambda: FastEmit regularisation (scales label gradients by 1+lambda).
         compact: ragged layout, STU = sum(frames_lengths * (labels_lengths + 1)).
     """
@@ -165,10 +219,23 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=
         costs = RNNTLossCompact.apply(log_probs.float(), labels, frames_lengths, labels_lengths, blank,
                                       fastemit_lambda,
                                       (log_probs.requires_grad and torch.is_grad_enabled()))
+    elif gather:
+        costs = RNNTLossGather.apply(log_probs, labels, frames_lengths, labels_lengths, blank, fastemit_lambda)
     else:
-        # gather=True and gather=False share the fused path: the log-prob gather happens inside
-        # the forward kernels, the dense scatter inside the backward kernel.
-        costs = RNNTLoss.apply(log_probs, labels, frames_lengths, labels_lengths, blank, fastemit_lambda, gather)
+        # dense path: the reduction below is folded into the one kernel launch (see RNNTLoss)
+        if reduction not in ("none", "mean", "sum", None):
+            raise ValueError(
+                f"Unknown reduction method: {reduction}, expected to be one of ['mean', 'sum', 'none']")
+        reduce = reduction in ("mean", "sum")
+        weights = None
+        if average_frames:
+            weights = 1.0 / frames_lengths.to(log_probs)
+        if reduction == "mean":
+            n = max(int(log_probs.size(0)), 1)
+            weights = torch.full((log_probs.size(0),), 1.0 / n, dtype=log_probs.dtype, device=log_probs.device) \
+                if weights is None else weights / n
+        return RNNTLoss.apply(log_probs, labels, frames_lengths, labels_lengths, blank, fastemit_lambda, weights,
+                              reduce)
 
     if average_frames:
         costs = costs / frames_lengths.to(log_probs)
@@ -184,5 +251,5 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=
             f"Unknown reduction method: {reduction}, expected to be one of ['mean', 'sum', 'none']")
 
 
-__all__ = ["rnnt_loss", "RNNTLoss", "RNNTLossEager", "RNNTLossCompact", "set_lse_mode", "core", "_C",
+__all__ = ["rnnt_loss", "RNNTLoss", "RNNTLossGather", "RNNTLossEager", "RNNTLossCompact", "compact_hints", "set_lse_mode", "core", "_C",
            "__version__"]

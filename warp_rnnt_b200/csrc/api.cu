@@ -198,6 +198,14 @@ int rnnt_b200_loss_dense(void *stream, void *workspace, size_t workspace_bytes, 
                          const int *labels, const int *xn, const int *yn, float *costs, float *grads,
                          const float *grad_scale, int N, int T, int U, int V, int blank, float fastemit_lambda,
                          int lse_mode) {
+    return rnnt_b200_loss_dense_reduced(stream, workspace, workspace_bytes, log_probs, labels, xn, yn, costs, grads,
+                                        grad_scale, nullptr, nullptr, N, T, U, V, blank, fastemit_lambda, lse_mode);
+}
+
+int rnnt_b200_loss_dense_reduced(void *stream, void *workspace, size_t workspace_bytes, const float *log_probs,
+                                 const int *labels, const int *xn, const int *yn, float *costs, float *grads,
+                                 const float *grad_scale, float *loss_sum, unsigned int *sync_counter, int N, int T,
+                                 int U, int V, int blank, float fastemit_lambda, int lse_mode) {
     if (!dense_args_ok(N, T, U, V) || blank < 0 || blank >= V) return RNNT_STATUS_INVALID_ARGUMENT;
     if (N == 0) return RNNT_STATUS_SUCCESS;
     cudaStream_t s = (cudaStream_t)stream;
@@ -205,8 +213,11 @@ int rnnt_b200_loss_dense(void *stream, void *workspace, size_t workspace_bytes, 
     FusedPlan plan;
     if (want_fused(N, T, U, &plan)) {
         RNNT_TRY(launch_fused(s, resolve_kind(lse_mode, false), plan, log_probs, labels, xn, yn, costs, grads, nullptr,
-                              grad_scale, N, T, U, V, blank, fastemit_lambda, 0, 1),
+                              grad_scale, N, T, U, V, blank, fastemit_lambda, 0, 1, nullptr, nullptr, nullptr, loss_sum,
+                              sync_counter),
                  RNNT_STATUS_WARP_FAILED);
+        if (loss_sum && !sync_counter)                  // no counter: reduce in a second, tiny launch
+            RNNT_TRY(launch_loss_sum(s, costs, grad_scale, N, loss_sum), RNNT_STATUS_COSTS_FAILED);
         return RNNT_STATUS_SUCCESS;
     }
     const Workspace w = carve(workspace, cells, N);
@@ -255,6 +266,8 @@ int rnnt_b200_loss_dense(void *stream, void *workspace, size_t workspace_bytes, 
                 cudaEventRecord(pl->join[2 + i], pl->wave_s[i]);
                 cudaStreamWaitEvent(s, pl->join[2 + i], 0);
             }
+            if (!status && loss_sum && launch_loss_sum(s, costs, grad_scale, N, loss_sum) != cudaSuccess)
+                status = RNNT_STATUS_COSTS_FAILED;
             return status;
         }
     }
@@ -268,6 +281,16 @@ int rnnt_b200_loss_dense(void *stream, void *workspace, size_t workspace_bytes, 
         src.scale = grad_scale; src.labels = labels; src.fastemit_lambda = fastemit_lambda;
         RNNT_TRY(launch_expand(s, p, src, grads, cells, V, blank), RNNT_STATUS_GRADS_BLANK_FAILED);
     }
+    if (loss_sum) RNNT_TRY(launch_loss_sum(s, costs, grad_scale, N, loss_sum), RNNT_STATUS_COSTS_FAILED);
+    return RNNT_STATUS_SUCCESS;
+}
+
+int rnnt_b200_rescale(void *stream, float *grads, const float *grad_out, int grad_out_stride, const float *applied,
+                      int N, int64_t elems_per_sample) {
+    if (N < 0 || elems_per_sample < 0 || grad_out_stride < 0 || grad_out_stride > 1 || !grads || !grad_out)
+        return RNNT_STATUS_INVALID_ARGUMENT;
+    RNNT_TRY(launch_rescale((cudaStream_t)stream, grads, grad_out, grad_out_stride, applied, N, elems_per_sample),
+             RNNT_STATUS_GRADS_BLANK_FAILED);
     return RNNT_STATUS_SUCCESS;
 }
 

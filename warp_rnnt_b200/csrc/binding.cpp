@@ -10,6 +10,7 @@
 // element); compact shapes are validated with one small device->host copy instead of four .item()s.
 // Extra entry points (rnnt_loss_dense, rnnt_gather_forward/backward) serve the fused python-level
 // paths of warp_rnnt_b200/__init__.py.
+#include <mutex>
 #include <string>
 #include <tuple>
 
@@ -58,11 +59,26 @@ void *current_stream(const at::Tensor &t) {
     return (void *)c10::cuda::getCurrentCUDAStream(t.device().index()).stream();
 }
 
-// dense forward (+ gradients), optional per-sample scale, explicit LSE mode
+// Tickets for the in-kernel loss reduction (rnnt_b200_loss_dense_reduced): a small ring of self-resetting device
+// counters per device, zeroed once; consecutive calls take consecutive slots so that calls running concurrently
+// on different streams (or captured into different CUDA graphs) never share one.
+unsigned int *next_sync_counter(const at::Tensor &like) {
+    constexpr int kSlots = 256, kMaxDev = 64;
+    static std::mutex mu;
+    static at::Tensor ring[kMaxDev];
+    static unsigned next[kMaxDev] = {};
+    const int dev = like.device().index();
+    if (dev < 0 || dev >= kMaxDev) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ring[dev].defined()) ring[dev] = at::zeros({kSlots}, like.options().dtype(at::kInt));
+    return reinterpret_cast<unsigned int *>(ring[dev].data_ptr<int>()) + (next[dev]++ % kSlots);
+}
+
+// dense forward (+ gradients), optional per-sample scale, explicit LSE mode; loss_sum: (1) tensor or undefined
 std::tuple<at::Tensor, at::Tensor> loss_dense_impl(const at::Tensor &xs, const at::Tensor &ys, const at::Tensor &xn,
                                                    const at::Tensor &yn, int blank, float fastemit_lambda,
                                                    const c10::optional<at::Tensor> &scale, bool want_grads,
-                                                   int lse_mode) {
+                                                   int lse_mode, at::Tensor loss_sum = at::Tensor()) {
     check4(xs, ys, xn, yn);
     check_dense_shapes(xs, ys, xn, yn);
     const c10::cuda::CUDAGuard guard(xs.device());
@@ -91,10 +107,12 @@ std::tuple<at::Tensor, at::Tensor> loss_dense_impl(const at::Tensor &xs, const a
     } else {
         TORCH_CHECK(blank >= 0 && blank < V, "blank must be in [0, V) (or -1 for the gathered layout)");
         at::Tensor ws = workspace_for(xs, N * T * U, N);
-        status = rnnt_b200_loss_dense(current_stream(xs), ws.data_ptr(), (size_t)ws.numel(), xs.data_ptr<float>(),
-                                      ys.data_ptr<int>(), xn.data_ptr<int>(), yn.data_ptr<int>(),
-                                      costs.data_ptr<float>(), want_grads ? grads.data_ptr<float>() : nullptr, sc,
-                                      (int)N, (int)T, (int)U, (int)V, blank, fastemit_lambda, lse_mode);
+        float *ls = loss_sum.defined() ? loss_sum.data_ptr<float>() : nullptr;
+        status = rnnt_b200_loss_dense_reduced(current_stream(xs), ws.data_ptr(), (size_t)ws.numel(), xs.data_ptr<float>(),
+                                              ys.data_ptr<int>(), xn.data_ptr<int>(), yn.data_ptr<int>(),
+                                              costs.data_ptr<float>(), want_grads ? grads.data_ptr<float>() : nullptr,
+                                              sc, ls, ls ? next_sync_counter(xs) : nullptr, (int)N, (int)T, (int)U,
+                                              (int)V, blank, fastemit_lambda, lse_mode);
         check_status(status);
     }
     return std::make_tuple(costs, grads);
@@ -110,7 +128,7 @@ std::tuple<at::Tensor, at::Tensor> rnnt_loss(const at::Tensor &xs, const at::Ten
 std::tuple<at::Tensor, at::Tensor, at::Tensor> rnnt_loss_compact(const at::Tensor &xs, const at::Tensor &ys,
                                                                  const at::Tensor &xn, const at::Tensor &yn,
                                                                  const int blank, const float fastemit_lambda,
-                                                                 const bool required_grad) {
+                                                                 const bool required_grad, int hint_T, int hint_U) {
     check4(xs, ys, xn, yn);
     TORCH_CHECK(xs.dim() == 2, "xs must have 2 dimensions");
     TORCH_CHECK(xn.dim() == 1 && yn.dim() == 1 && xn.size(0) == yn.size(0), "xn and yn shape must be equal (N,)");
@@ -125,8 +143,12 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> rnnt_loss_compact(const at::Tenso
     at::Tensor grads = required_grad ? at::empty({STU, 2}, xs.options()) : at::empty({0}, xs.options());
     if (N == 0) return std::make_tuple(costs, grads, loc);
     int max_T = 0, max_U = 0;
-    // shape validation: one 16-byte device->host copy (the reference needs four .item() syncs)
-    {
+    // shape validation: one 16-byte device->host copy (the reference needs four .item() syncs) -- or none at all
+    // when the caller vouches for upper bounds of xn and yn+1 (sync-free, CUDA-graph capturable)
+    if (hint_T > 0 && hint_U > 0) {
+        max_T = hint_T;
+        max_U = hint_U;
+    } else {
         at::Tensor scratch = at::empty({2 * N}, xs.options().dtype(at::kLong));
         at::Tensor totals = at::empty({4}, xs.options().dtype(at::kInt));
         check_status(rnnt_b200_compact_totals(stream, xn.data_ptr<int>(), yn.data_ptr<int>(), (int)N,
@@ -186,6 +208,43 @@ std::tuple<at::Tensor, at::Tensor> rnnt_loss_dense(const at::Tensor &xs, const a
     return loss_dense_impl(xs, ys, xn, yn, blank, fastemit_lambda, grad_scale, want_grads, lse_mode);
 }
 
+// loss + dense gradients + reduced loss in one call: (costs (N), grads like xs or empty, loss (1) = sum costs*scale)
+std::tuple<at::Tensor, at::Tensor, at::Tensor> rnnt_loss_fused(const at::Tensor &xs, const at::Tensor &ys,
+                                                               const at::Tensor &xn, const at::Tensor &yn, int blank,
+                                                               float fastemit_lambda,
+                                                               const c10::optional<at::Tensor> &grad_scale,
+                                                               bool want_grads, int lse_mode) {
+    TORCH_CHECK(blank >= 0, "rnnt_loss_fused takes the dense (N,T,U,V) layout");
+    TORCH_CHECK(xs.device().is_cuda(), "xs must be located in the CUDA");
+    const c10::cuda::CUDAGuard guard(xs.device());
+    at::Tensor loss = at::empty({1}, xs.options().dtype(at::kFloat));
+    if (xs.dim() == 4 && xs.size(0) == 0) loss.zero_();
+    auto r = loss_dense_impl(xs, ys, xn, yn, blank, fastemit_lambda, grad_scale, want_grads, lse_mode, loss);
+    return std::make_tuple(std::get<0>(r), std::get<1>(r), loss);
+}
+
+// in place: grads[n] *= grad_out[n] / applied[n] where they differ (grad_out with one element: one scalar for all)
+void rnnt_rescale_(at::Tensor grads, const at::Tensor &grad_out, const c10::optional<at::Tensor> &applied) {
+    TORCH_CHECK(grads.is_contiguous() && grads.scalar_type() == at::ScalarType::Float && grads.device().is_cuda() &&
+                    grads.dim() >= 1,
+                "grads must be a contiguous CUDA Float tensor");
+    const int64_t N = grads.size(0);
+    TORCH_CHECK(grad_out.is_contiguous() && grad_out.scalar_type() == at::ScalarType::Float &&
+                    grad_out.device() == grads.device() && (grad_out.numel() == N || grad_out.numel() == 1),
+                "grad_out must be a contiguous Float tensor with N elements (or one) on the device of grads");
+    const float *ap = nullptr;
+    if (applied.has_value() && applied->defined()) {
+        TORCH_CHECK(applied->is_contiguous() && applied->scalar_type() == at::ScalarType::Float &&
+                        applied->device() == grads.device() && applied->numel() == N,
+                    "applied must be a contiguous Float tensor of shape (N,) on the device of grads");
+        ap = applied->data_ptr<float>();
+    }
+    if (N == 0) return;
+    const c10::cuda::CUDAGuard guard(grads.device());
+    check_status(rnnt_b200_rescale(current_stream(grads), grads.data_ptr<float>(), grad_out.data_ptr<float>(),
+                                   (grad_out.numel() == 1 && N != 1) ? 0 : 1, ap, (int)N, grads.numel() / N));
+}
+
 std::tuple<at::Tensor, at::Tensor> rnnt_gather_forward(const at::Tensor &xs, const at::Tensor &ys,
                                                        const at::Tensor &xn, const at::Tensor &yn, int blank,
                                                        float fastemit_lambda, bool want_grads, int lse_mode) {
@@ -235,13 +294,17 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("xn"), py::arg("yn"), py::arg("blank") = 0, py::arg("fastemit_lambda") = 0.0);
     m.def("rnnt_loss_compact", &rnnt_loss_compact, "B200 RNN-Transducer loss in compact layout.", py::arg("xs"),
           py::arg("ys"), py::arg("xn"), py::arg("yn"), py::arg("blank") = 0, py::arg("fastemit_lambda") = 0.0,
-          py::arg("required_grad") = true);
+          py::arg("required_grad") = true, py::arg("max_T") = 0, py::arg("max_U") = 0);
     m.def("rnnt_loss_compact_backward", &rnnt_loss_compact_backward,
           "B200 RNN-Transducer loss backward for compact layout", py::arg("grad_costs"), py::arg("grad_xs"),
           py::arg("cumSum"), py::arg("loc"), py::arg("V"), py::arg("blank") = 0);
     m.def("rnnt_loss_dense", &rnnt_loss_dense, py::arg("xs"), py::arg("ys"), py::arg("xn"), py::arg("yn"),
           py::arg("blank") = 0, py::arg("fastemit_lambda") = 0.0, py::arg("grad_scale") = py::none(),
           py::arg("want_grads") = true, py::arg("lse_mode") = 0);
+    m.def("rnnt_loss_fused", &rnnt_loss_fused, py::arg("xs"), py::arg("ys"), py::arg("xn"), py::arg("yn"),
+          py::arg("blank") = 0, py::arg("fastemit_lambda") = 0.0, py::arg("grad_scale") = py::none(),
+          py::arg("want_grads") = true, py::arg("lse_mode") = 0);
+    m.def("rnnt_rescale_", &rnnt_rescale_, py::arg("grads"), py::arg("grad_out"), py::arg("applied") = py::none());
     m.def("rnnt_gather_forward", &rnnt_gather_forward, py::arg("xs"), py::arg("ys"), py::arg("xn"), py::arg("yn"),
           py::arg("blank") = 0, py::arg("fastemit_lambda") = 0.0, py::arg("want_grads") = true,
           py::arg("lse_mode") = 0);

@@ -164,6 +164,63 @@ k_expand(Problem p, ExpandSrc src, float *__restrict__ out, int64_t cells, int V
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_loss_sum: loss = sum_n costs[n] * scale[n] in a fixed order (general path; the fused kernel does this itself).
+// k_rescale : grads[n] *= grad_out[n] / applied[n] where they differ -- RNNTLoss.backward's mul_
+//             (__init__.py:21-24) reduced to a no-op for the usual case that the upstream gradient is what the
+//             forward already multiplied in (a CTA whose sample needs no change returns at once, no memory traffic).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_loss_sum(const float *__restrict__ costs, const float *__restrict__ scale, int N,
+                                                 float *__restrict__ loss_sum) {
+    const int lane = threadIdx.x;
+    float acc = 0.0f;
+    for (int i = lane; i < N; i += 32) acc += scale ? costs[i] * scale[i] : costs[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) *loss_sum = acc;
+}
+
+constexpr int kRescaleThreads = 256;
+__global__ void __launch_bounds__(kRescaleThreads)
+k_rescale(float *__restrict__ grads, const float *__restrict__ grad_out, int go_stride, const float *__restrict__ applied,
+          int64_t elems) {
+    const int n = blockIdx.y;
+    const float target = grad_out[(int64_t)n * go_stride];
+    const float cur = applied ? applied[n] : 1.0f;
+    if (target == cur) return;                              // already what the forward multiplied in
+    const float f = (cur == 1.0f) ? target : target / cur;  // cur == 1: exactly the reference's grads * grad_output
+    float *g = grads + (int64_t)n * elems;
+    const bool vec = ((reinterpret_cast<uintptr_t>(g) & 15u) == 0);
+    const int64_t n4 = vec ? elems / 4 : 0;
+    float4 *g4 = reinterpret_cast<float4 *>(g);
+    for (int64_t i = (int64_t)blockIdx.x * kRescaleThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kRescaleThreads) {
+        float4 v = g4[i];
+        v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+        g4[i] = v;
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * kRescaleThreads + threadIdx.x; i < elems; i += (int64_t)gridDim.x * kRescaleThreads)
+        g[i] *= f;
+}
+
+cudaError_t launch_loss_sum(cudaStream_t s, const float *costs, const float *scale, int N, float *loss_sum) {
+    k_loss_sum<<<1, 32, 0, s>>>(costs, scale, N, loss_sum);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rescale(cudaStream_t s, float *grads, const float *grad_out, int grad_out_stride, const float *applied,
+                           int N, int64_t elems_per_sample) {
+    if (N <= 0 || elems_per_sample <= 0) return cudaSuccess;
+    const int sms = sm_count(current_device());
+    int64_t gx = (elems_per_sample / 4 + kRescaleThreads * 8 - 1) / (kRescaleThreads * 8);
+    const int64_t cap = ((int64_t)sms * 8 + N - 1) / N;
+    gx = max((int64_t)1, min(gx, cap));
+    dim3 grid((unsigned)gx, (unsigned)N);
+    k_rescale<<<grid, kRescaleThreads, 0, s>>>(grads, grad_out, grad_out_stride, applied, elems_per_sample);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src, float *out, int64_t cells,
                           int V, int blank, bool retire_early) {
     if (cells <= 0) return cudaSuccess;

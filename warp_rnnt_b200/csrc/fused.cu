@@ -176,6 +176,31 @@ __device__ __forceinline__ void sts_vec(uint32_t a, const float (&v)[C]) {
     }
 }
 
+// Fused loss reduction (replaces the separate costs.sum() pass of __init__.py:132-143 and, through `scale`,
+// average_frames / 'mean'): every reporting CTA's warp 0 calls this after its thread 0 wrote costs[n]; the LAST caller
+// (device counter) adds costs[0..N) * scale[0..N) in a fixed order -- lane-strided partial sums, then a shuffle tree --
+// so the result is deterministic (no float atomics).  The counter is left at 0 for the next launch.
+__device__ __forceinline__ void loss_reduce_last(const float *costs, const float *scale, int N, float *loss_sum,
+                                                 unsigned *counter) {
+    const int lane = threadIdx.x & 31;
+    unsigned last = 0;
+    if (lane == 0) {
+        __threadfence();                                    // costs[n] before the ticket
+        last = (atomicAdd(counter, 1u) == (unsigned)(N - 1)) ? 1u : 0u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();                                        // the other CTAs' costs after the ticket
+    float acc = 0.0f;
+    for (int i = lane; i < N; i += 32) {
+        const float c = __ldcg(costs + i);
+        acc += scale ? c * __ldcg(scale + i) : c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) { *loss_sum = acc; *counter = 0u; }
+}
+
 struct FusedArgs {
     const float *lp;        // dense (N,T,U,V) or, pairs_in, (N,T,U,2)
     const int *labels;      // (N,U-1); compact: (sum yn)
@@ -196,6 +221,8 @@ struct FusedArgs {
     int gw;                 // warps that gather (of the 14 non-wavefront warps); MODE 0: the rest start the zero-fill at once
     int tma_fill;           // MODE 0: zero-fill with bulk shared->global copies (else 256-bit STG)
     long long *trace;       // optional per-CTA phase stamps (clock64), 8 per CTA; null = off
+    float *loss_sum;        // optional: sum_n costs[n] * (scale ? scale[n] : 1), written by the last CTA to finish
+    unsigned *sync_counter; // with loss_sum: device counter, 0 on entry, left 0 (self-resetting)
     int poison_n;           // test hook: sample whose alpha-side ll gets poison_delta added before the guard (-1 = off)
     float poison_delta;
 };
@@ -602,6 +629,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         }
         if (slice == 0) A.costs[n] = cost;
     }
+    if (A.loss_sum && slice == 0 && warp == 0) loss_reduce_last(A.costs, A.scale, A.N, A.loss_sum, A.sync_counter);
     __syncthreads();
     const bool live = ok && !s_bad;
     const float b00 = live ? BE[idxB(0, 0)] : 0.0f;
@@ -777,8 +805,10 @@ static cudaError_t launch_fused_km(cudaStream_t s, const FusedArgs &a, size_t sm
 cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const float *lp, const int *labels,
                          const int *xn, const int *yn, float *costs, float *grads, float2 *pair_grads,
                          const float *scale, int N, int T, int U, int V, int blank, float lam, int pairs_in,
-                         int guard, const int64_t *mem_pref, const int64_t *lab_pref, int64_t *loc) {
+                         int guard, const int64_t *mem_pref, const int64_t *lab_pref, int64_t *loc, float *loss_sum,
+                         unsigned *sync_counter) {
     FusedArgs a;
+    a.loss_sum = sync_counter ? loss_sum : nullptr; a.sync_counter = sync_counter;
     a.mem_pref = mem_pref; a.lab_pref = lab_pref; a.loc = loc;
     a.lp = lp; a.labels = labels; a.xn = xn; a.yn = yn; a.costs = costs; a.grads = grads; a.pair_grads = pair_grads;
     a.scale = scale; a.N = N; a.T = T; a.U = U; a.V = V; a.blank = blank; a.lam = lam; a.pairs_in = pairs_in;

@@ -48,6 +48,12 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
                          const int *xn, const int *yn, float *costs, float *grads, float2 *pair_grads,
                          const float *scale, int N, int T, int U, int V, int blank, float lam, int pairs_in,
                          int guard, const int64_t *mem_pref = nullptr, const int64_t *lab_pref = nullptr,
-                         int64_t *loc = nullptr);   // mem_pref != null: compact layout, T/U = max lengths
+                         int64_t *loc = nullptr,   // mem_pref != null: compact layout, T/U = max lengths
+                         float *loss_sum = nullptr, unsigned *sync_counter = nullptr);   // fused sum_n costs[n]*scale[n]
+
+// expand.cu -- small helpers of the python-level API
+cudaError_t launch_loss_sum(cudaStream_t s, const float *costs, const float *scale, int N, float *loss_sum);
+cudaError_t launch_rescale(cudaStream_t s, float *grads, const float *grad_out, int grad_out_stride,
+                           const float *applied, int N, int64_t elems_per_sample);
 
 }  // namespace rnnt

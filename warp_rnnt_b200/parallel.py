@@ -61,15 +61,57 @@ def all_reduce_loss(local_sum, local_count, reduction="mean", group=None):
 
 def rnnt_loss_sharded(log_probs, labels, frames_lengths, labels_lengths, average_frames=False,
                       reduction="mean", blank=0, gather=False, fastemit_lambda=0.0, compact=False,
-                      group=None, loss_fn=None):
+                      group=None, loss_fn=None, global_batch=None):
     """Loss over a batch that is sharded across the ranks of ``group``.
 
     Arguments are this rank's shard (same meaning as ``rnnt_loss``).  Returns the GLOBAL reduced
     loss, identical on every rank; ``.backward()`` leaves d(global loss)/d(local log_probs) in
-    ``log_probs.grad`` (gradients never cross GPUs)."""
+    ``log_probs.grad`` (gradients never cross GPUs).
+
+    The local part is ONE call of ``rnnt_loss(reduction='sum')`` -- on the dense path one kernel launch that also
+    returns the local sum -- followed by one all-reduce of 1 element ('sum', or 'mean' with ``global_batch`` =
+    the number of lattices over all ranks known to the caller) or 2 elements ('mean' otherwise: sum and count)."""
+    if reduction not in ("sum", "mean"):
+        raise ValueError("sharded loss supports reduction 'sum' or 'mean', got %r" % (reduction,))
     if loss_fn is None:
         from . import rnnt_loss as loss_fn
-    costs = loss_fn(log_probs, labels, frames_lengths, labels_lengths, average_frames=average_frames,
-                    reduction="none", blank=blank, gather=gather, fastemit_lambda=fastemit_lambda,
+    local = loss_fn(log_probs, labels, frames_lengths, labels_lengths, average_frames=average_frames,
+                    reduction="sum", blank=blank, gather=gather, fastemit_lambda=fastemit_lambda,
                     compact=compact)
-    return all_reduce_loss(costs.sum(), int(costs.shape[0]), reduction, group)
+    n_local = int(frames_lengths.shape[0])
+    if reduction == "mean" and global_batch is not None:
+        return all_reduce_loss(local, n_local, "sum", group) / float(global_batch)
+    return all_reduce_loss(local, n_local, reduction, group)
+
+
+def rnnt_loss_microbatches(batches, global_batch, reduction="mean", average_frames=False, blank=0, gather=False,
+                           fastemit_lambda=0.0, compact=False, group=None, loss_fn=None):
+    """One training step over a rank-local batch that is too large for one call (BASELINE configs[4]: 256 lattices
+    of 600 x 150 x 1024 per GPU are 94 GB of log-probs plus 94 GB of gradients), processed as micro-batches.
+
+    ``batches`` yields ``(log_probs, labels, frames_lengths, labels_lengths)`` micro-batches of this rank (lattices are
+    independent).  Each one runs ``rnnt_loss(..., reduction='sum')`` and its ``backward()`` at once, so
+    only one micro-batch's gradient is being produced at a time; the weight 1/global_batch of reduction='mean' is
+    applied to the returned value AND, through the upstream gradient of each backward, to the gradients.  The step ends
+    with ONE all-reduce of the scalar.  Returns the global loss (detached; the gradients are already in
+    ``log_probs.grad`` of every micro-batch that required grad)."""
+    if reduction not in ("sum", "mean"):
+        raise ValueError("reduction must be 'sum' or 'mean', got %r" % (reduction,))
+    if loss_fn is None:
+        from . import rnnt_loss as loss_fn
+    scale = 1.0 / float(global_batch) if reduction == "mean" else 1.0
+    total = None
+    for log_probs, labels, frames_lengths, labels_lengths in batches:
+        loss = loss_fn(log_probs, labels, frames_lengths, labels_lengths, average_frames=average_frames,
+                       reduction="sum", blank=blank, gather=gather, fastemit_lambda=fastemit_lambda, compact=compact)
+        if loss.requires_grad:
+            (loss * scale).backward() if scale != 1.0 else loss.backward()
+        total = loss.detach() if total is None else total + loss.detach()
+    if total is None:
+        raise ValueError("no micro-batches")
+    total = total * scale
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        total = total.reshape(1).clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        total = total[0]
+    return total
