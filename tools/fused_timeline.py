@@ -15,7 +15,8 @@ import torch  # noqa: E402
 import warp_rnnt_b200 as w  # noqa: E402
 
 SHAPES = {"c2": (128, 150, 40, 28), "c2n32": (32, 150, 40, 28), "c2n148": (148, 150, 40, 28), "c3": (32, 150, 20, 5000), "c1": (1, 150, 40, 28)}
-NAMES = ["start", "sentinels", "gather_done", "sweep_start", "alpha_done", "beta_done", "fill_done", "end"]
+NAMES = ["start", "sentinels", "gather_done", "sweep_start", "alpha_done", "beta_done", "fill_issued", "end", "chase_done",
+         "zeros_landed", "patch_start"]
 
 
 def sm_mhz():
@@ -60,7 +61,7 @@ def main():
         mhz = max(mhz, sm_mhz())
         tr = trace.view(-1, 16).cpu()
         tr = tr[tr[:, 0] > 0]
-        rel = (tr[:, :8] - tr[:, :1]).clamp(min=0).double() / mhz          # cycles / MHz = us
+        rel = (tr[:, :len(NAMES)] - tr[:, :1]).clamp(min=0).double() / mhz          # cycles / MHz = us
         med = rel.median(dim=0).values.tolist()
         mx = rel.max(dim=0).values.tolist()
         out[mode] = {"ctas": int(tr.shape[0]), "sm_mhz": mhz, "event_us": e0.elapsed_time(e1) * 1e3,

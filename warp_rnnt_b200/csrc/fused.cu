@@ -216,6 +216,7 @@ struct FusedArgs {
     int pairs_in, guard, slices;
     int zoff;               // byte offset of the zero buffer in dynamic shared memory
     int nbuf, row_off, row_stride;   // TMA row gather: buffers (0 = LDG gather), their byte offset and stride
+    int gwn, nb_per;        // TMA row gather: gather warps and row buffers per warp (nbuf = gwn * nb_per)
     int Wd;                 // staged row stride (floats) = C * ceil(U / C), even
     int nd;                 // staged rows (diagonals) allocated = T + Wd + 16
     int gw;                 // warps that gather (of the 14 non-wavefront warps); MODE 0: the rest start the zero-fill at once
@@ -247,10 +248,18 @@ __device__ __forceinline__ float shfl_up1_ordered(float v) {
     return r;
 }
 
-template <int KIND, int C>
+// ALPHA: the operands come from the BETA-side planes (one staged copy of the log-probs serves both directions; the
+// shared memory this saves holds more TMA row buffers).  An anti-diagonal t+u = e is ONE row of the beta layout,
+// r(e) = T1 + Wd - 1 - e, with the columns reversed (j' = Wd-1-u).  Alpha's step e needs the blank edges of the cells
+// on diagonal e-1 -> row r(e)+1, walked DOWNWARDS (negative stride), the lane's C columns as one reversed vector; its
+// label edges sit one column further (lp_l[t,u-1] at j'+1): the aligned vector supplies C-1 of them and the lane to
+// the left the last one (one extra shuffle per step, off the dependent chain; lattice column 0 has no label edge).
+// `prog`: diagonals completed so far, published (st.release) once per loop iteration for the warps that chase the
+// wavefronts (see k_fused, "chase").
+template <int KIND, int C, bool ALPHA>
 __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t out, int Wd, int ndiag, int lane,
                                            int first_col, const float *pre, int pre_rows, GatherWait gw,
-                                           uint32_t scratch) {
+                                           uint32_t scratch, int *prog, int row0) {
     constexpr int P = (C <= 2) ? 4 : 2;                       // diagonals of operand prefetch = steps per loop iteration
     float val[C];
 #pragma unroll
@@ -263,7 +272,32 @@ __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t ou
     uint32_t stride = 4u * (uint32_t)Wd;
     asm volatile("" : "+r"(stride));
     const uint32_t off = 4u * (uint32_t)(C * lane);
-    uint32_t a_wb = wb + off, a_wl = wl + off, a_out = out + off;
+    // operand addresses.  beta: row 0 upwards, columns C*lane..  alpha: row `row0` = T1 + Wd downwards, columns
+    // Wd - C*(lane+1).. (reversed); lanes past the staged row read neighbouring rows (finite garbage, never used)
+    const uint32_t opoff = ALPHA ? (uint32_t)(4 * (row0 * Wd + Wd - C * (lane + 1))) : off;
+    uint32_t a_wb = wb + opoff, a_wl = wl + opoff, a_out = out + off;
+    const uint32_t ostride = ALPHA ? (0u - stride) : stride;
+    // one diagonal's operands into b[k], l[k] (alpha: reversed vector + the left lane's first element)
+    auto fetch = [&](float (&bk)[C], float (&lk)[C]) {
+        if constexpr (ALPHA) {
+            float vb[C], vl[C];
+            lds_vec<C>(a_wb, vb);
+            lds_vec<C>(a_wl, vl);
+            float edge;
+            asm volatile("shfl.sync.up.b32 %0, %1, 1, 0, 0xffffffff;" : "=f"(edge) : "f"(vl[0]) : "memory");
+            if (lane == 0) edge = kBigF;                       // lattice column 0: no label edge
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                bk[c] = vb[C - 1 - c];
+                lk[c] = (c == 0) ? edge : vl[C - c];
+            }
+        } else {
+            lds_vec<C>(a_wb, bk);
+            lds_vec<C>(a_wl, lk);
+        }
+        a_wb += ostride;
+        a_wl += ostride;
+    };
     // exact mode: the first real column is taken from the reference-order prefix scan (core.cu:92-110)
     const int l0 = first_col / C, c0 = first_col - l0 * C;
     // Predicate registers are scarce (7 per thread) and each exact-LSE chain keeps 3 alive; with more in the
@@ -274,6 +308,7 @@ __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t ou
 #pragma unroll
     for (int c = 0; c < C; ++c) own[c] = ((KIND != kFast) && lane == l0 && c == c0) ? 0xffffffffu : 0u;
     const uint32_t a_pre = (uint32_t)__cvta_generic_to_shared(pre);
+    const uint32_t a_prog = (uint32_t)__cvta_generic_to_shared(prog);
     auto pre_at = [&](int d) -> float {                      // scan value for diagonal d (clamped; unused when out of range)
         const int i = min(max(d - first_col, 0), pre_rows - 1);
         float v;
@@ -290,11 +325,8 @@ __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t ou
     gw.ensure(P - 1);                                         // diagonals 0..P-1 touch rows <= P-1
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-        lds_vec<C>(a_wb, b[k]);
-        lds_vec<C>(a_wl, l[k]);
+        fetch(b[k], l[k]);
         if (KIND != kFast) pv[k] = pre_at(k);
-        a_wb += stride;
-        a_wl += stride;
     }
     // Exact LSE: ptxas interleaves the lane's C chains in every step of the unrolled body except the last one
     // before the back-edge (and in none of them if the loop also contains a conditional store, e.g. a trace
@@ -329,14 +361,15 @@ __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t ou
             for (int c = 0; c < C; ++c) val[c] = nv[c];
             sts_vec<C>(a_out, val);                          // (lanes past the staged row: scratch slot, stride 0)
             a_out += stride_out;
-            lds_vec<C>(a_wb, b[k]);                            // operands P diagonals ahead (rows past ndiag are allocated)
-            lds_vec<C>(a_wl, l[k]);
+            fetch(b[k], l[k]);                                 // operands P diagonals ahead (rows past ndiag are allocated)
             if (KIND != kFast) pv[k] = pre_at(d0 + k + P);
-            a_wb += stride;
-            a_wl += stride;
         }
       }
+        // progress for the chasing warps: diagonals < d00 + H*P are complete and their operands consumed (every lane
+        // stores the same word: an unconditional store keeps the loop free of predicated side exits)
+        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a_prog), "r"(d00 + H * P) : "memory");
     }
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a_prog), "r"(0x3fffffff) : "memory");
 }
 
 // MODE 0: dense gradients (zero-fill + patch).  MODE 1: (N,T,U,2) gradients.  Both write costs.
@@ -350,17 +383,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     const bool ok = (Tn >= 1 && Tn <= T && Un >= 1 && Un <= U);
     const int T1 = Tn - 1, U1 = Un - 1;
 
-    // ---- shared memory carve-up: five diagonal-major arrays [nd][Wd], prefix-scan columns, labels
+    // ---- shared memory carve-up: four diagonal-major planes [nd][Wd], prefix-scan columns, labels.
+    // ONE staged copy of the log-probs (beta-side indexing) serves both wavefronts; alpha walks it backwards.
+    // Plane order matters: alpha's prefetch past its last diagonal reads a few rows BELOW row 0 of WBb / WLb, which
+    // must still be shared memory (it lands in the plane before; the values are never used).
     const size_t plane = (size_t)A.nd * Wd;
-    float *WBa = reinterpret_cast<float *>(smem_raw);   // alpha: blank edge into (t,u)   at [t+u][u]
-    float *WLa = WBa + plane;                           // alpha: label edge into (t,u)   at [t+u][u]
-    float *WBb = WLa + plane;                           // beta : blank edge out of (t,u) at [d'][j'], j' = Wd-1-u, d' = (T1-t)+j'
-    float *WLb = WBb + plane;                           // beta : label edge out of (t,u) at [d'][j']
-    float *AL = WLa;                                    // alpha[t,u] at [t+u][u]: IN PLACE over its label edges -- the
-                                                        // wavefront has read slot [d][j] P steps before it writes it;
-                                                        // phase 2 takes the log-probs from the beta-side copies
-    float *BE = WLb + plane;                            // beta[t,u]  at [d'][j']
-    float *preA = BE + plane;                           // [T] exact-mode column scans
+    float *AL = reinterpret_cast<float *>(smem_raw);    // alpha[t,u] at [t+u][u]
+    float *BE = AL + plane;                             // beta[t,u]  at [d'][j'], j' = Wd-1-u, d' = (T1-t)+j'
+    float *WBb = BE + plane;                            // blank edge out of (t,u) at [d'][j']; after the chase: alpha+beta+lp
+    float *WLb = WBb + plane;                           // label edge out of (t,u) at [d'][j']; after the chase: alpha+beta+lp
+    float *preA = WLb + plane;                          // [T] exact-mode column scans
     float *preB = preA + T;
     int *s_lab = reinterpret_cast<int *>(preB + T);     // [U]
     // zero buffer for the bulk fill: the last kZeroBytes of the dynamic allocation (128-byte aligned)
@@ -369,7 +401,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     __shared__ int s_next;                              // fill work counter
     __shared__ int s_bad;
     __shared__ int s_flag[kMaxChunks];                  // gather chunk q staged / rows finished by gather warp g
-    __shared__ __align__(8) unsigned long long s_bar[kMaxRowBufs];   // TMA row gather: one mbarrier per buffer
+    __shared__ int s_prog[2];                           // diagonals completed by the alpha / beta wavefront
+    __shared__ __align__(8) unsigned long long s_bar[2 * kMaxRowBufs];   // TMA row gather: one mbarrier per buffer
     long long *trace = A.trace ? A.trace + 16 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
     auto stamp = [&](int slot) {                        // latest arrival per phase
         if (trace && lane == 0) atomicMax(reinterpret_cast<unsigned long long *>(trace) + slot, (unsigned long long)clock64());
@@ -390,7 +423,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     const bool use_tma = A.nbuf > 0 && (!compact || ((((slab * V) | ((int64_t)Un * V)) & 3) == 0));
 
     // ---- phase 0: sentinels, labels, gather
-    if (tid == 0) { s_next = 0; s_bad = ok ? 0 : 1; }
+    if (tid == 0) { s_next = 0; s_bad = ok ? 0 : 1; s_prog[0] = 0; s_prog[1] = 0; }
     if (tid < kMaxChunks) s_flag[tid] = 0;
     if (tid < A.nbuf) mbar_init((uint32_t)__cvta_generic_to_shared(&s_bar[tid]), 1);
     if (A.nbuf > 0) {                                   // make the initialised barriers visible to the async proxy (TMA)
@@ -406,8 +439,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         const int lim4 = min((used + 3) >> 2, (int)(plane >> 2));   // planes are whole float4s (nd, Wd even)
         const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), b4 = make_float4(kBigF, kBigF, kBigF, kBigF);
         for (int k = tid; k < lim4; k += kFusedThreads) {
-            reinterpret_cast<float4 *>(WBa)[k] = z4; reinterpret_cast<float4 *>(WBb)[k] = z4;
-            reinterpret_cast<float4 *>(WLa)[k] = b4; reinterpret_cast<float4 *>(WLb)[k] = b4;
+            reinterpret_cast<float4 *>(WBb)[k] = z4;
+            reinterpret_cast<float4 *>(WLb)[k] = b4;
         }
         if (!A.pairs_in)
             for (int u = tid; u < U1; u += kFusedThreads) s_lab[u] = A.labels[lab0 + u];
@@ -426,38 +459,48 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     const int cells_n = ok ? Tn * Un : 0;
     const int nchunks = (cells_n + kChunkCells - 1) >> kChunkLog;
     if (use_tma) {
-        // TMA row gather: gather warp g owns row buffer g and stages order-rows g, g+nbuf, ...
-        if (ok && lw >= 2 && lw < 2 + A.nbuf) {
-            const int g = lw - 2;
-            const float *buf = reinterpret_cast<const float *>(smem_raw + A.row_off + (size_t)g * A.row_stride);
-            const uint32_t buf_s = (uint32_t)__cvta_generic_to_shared(buf);
-            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[g]);
+        // TMA row gather: gather warp g of `gwn` stages order-rows g, g+gwn, ... through its own `nb_per` row buffers
+        // (two when they fit: the next row is already in flight while this one is picked apart)
+        if (ok && lw >= 2 && lw < 2 + A.gwn) {
+            const int g = lw - 2, NB = A.nb_per;
             const uint64_t pol_first = policy_evict_first();
             const uint32_t bytes = ((uint32_t)(Un * V) * 4u + 15u) & ~15u;   // <= U*V*4, which is a multiple of 16
-            uint32_t phase = 0;
-            int done = 0;
-            for (int k = g; k < Tn; k += A.nbuf) {
-                const int t = (k & 1) ? T1 - (k >> 1) : (k >> 1);   // rows alternate: top, bottom, top, ...
+            auto buf_of = [&](int slot) { return reinterpret_cast<const float *>(smem_raw + A.row_off + (size_t)(g * NB + slot) * A.row_stride); };
+            auto row_of = [&](int k) { return (k & 1) ? T1 - (k >> 1) : (k >> 1); };   // rows alternate: top, bottom, top, ...
+            auto issue = [&](int k, int slot) {
                 if (lane == 0) {
+                    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[g * NB + slot]);
                     mbar_expect_tx(bar, bytes);
-                    bulk_load(buf_s, A.lp + (slab + (int64_t)t * RS) * V, bytes, bar, pol_first);
+                    bulk_load((uint32_t)__cvta_generic_to_shared(buf_of(slot)), A.lp + (slab + (int64_t)row_of(k) * RS) * V, bytes, bar, pol_first);
                 }
-                while (!mbar_try_wait(bar, phase)) {}
-                phase ^= 1u;
+            };
+            for (int j = 0; j < NB; ++j)
+                if (g + j * A.gwn < Tn) issue(g + j * A.gwn, j);
+            uint32_t phases = 0;                        // bit `slot` = parity to wait for
+            int done = 0, slot = 0;
+            for (int k = g; k < Tn; k += A.gwn) {
+                const int t = row_of(k);
+                const float *buf = buf_of(slot);
+                const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[g * NB + slot]);
+                // lane 0 waits for the copy, the warp converges behind it (one poller per barrier)
+                if (lane == 0) while (!mbar_try_wait(bar, (phases >> slot) & 1u)) {}
+                __syncwarp();
+                phases ^= 1u << slot;
                 for (int u = lane; u < Un; u += 32) {
                     const float vb = buf[u * V + A.blank];
                     const float vl = (u < U1) ? buf[u * V + s_lab[u]] : kBigF;
                     const int ib = idxB(t, u);
                     WBb[ib] = vb;
                     WLb[ib] = vl;                       // kBig on the last column: beta's first column has no column edge
-                    if (t < T1) WBa[idxA(t + 1, u)] = vb;
-                    if (u < U1) WLa[idxA(t, u + 1)] = vl;
                 }
                 __syncwarp();                           // every lane is done with the buffer and has staged its cells
+                const int kn = k + NB * A.gwn;          // refill this buffer with the row NB turns ahead
+                if (kn < Tn) issue(kn, slot);
                 if (lane == 0) {
                     ++done;
                     asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_flag[g])), "r"(done) : "memory");
                 }
+                slot = (slot + 1 == NB) ? 0 : slot + 1;
             }
             stamp(2);
         }
@@ -500,8 +543,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
                     const int ib = idxB(t, u);
                     WBb[ib] = vb[g];
                     WLb[ib] = vl[g];                    // kBig on the last column: beta's first column has no column edge
-                    if (t < T1) WBa[idxA(t + 1, u)] = vb[g];
-                    if (u < U1) WLa[idxA(t, u + 1)] = vl[g];
                 }
             }
             __syncwarp();
@@ -551,14 +592,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
             }
             __syncwarp();
         }
-        const uint32_t wb_a = (uint32_t)__cvta_generic_to_shared(beta ? WBb : WBa);
-        const uint32_t wl_a = (uint32_t)__cvta_generic_to_shared(beta ? WLb : WLa);
+        const uint32_t wb_a = (uint32_t)__cvta_generic_to_shared(WBb);
+        const uint32_t wl_a = (uint32_t)__cvta_generic_to_shared(WLb);
         const uint32_t out_a = (uint32_t)__cvta_generic_to_shared(beta ? BE : AL);
         GatherWait gwait;
-        gwait.flag = s_flag; gwait.Un = Un; gwait.Tn = Tn; gwait.ready = 0; gwait.lane = lane; gwait.gwn = use_tma ? A.nbuf : 0; gwait.m_ok = -1;
+        gwait.flag = s_flag; gwait.Un = Un; gwait.Tn = Tn; gwait.ready = 0; gwait.lane = lane; gwait.gwn = use_tma ? A.gwn : 0; gwait.m_ok = -1;
         stamp(3);
-        sweep_diag<KIND, C>(wb_a, wl_a, out_a, Wd, ndiag, lane, first_col, pre, Tn, gwait,
-                            (uint32_t)__cvta_generic_to_shared(&s_scratch[lw][0]));
+        const uint32_t scr = (uint32_t)__cvta_generic_to_shared(&s_scratch[lw][0]);
+        if (beta) sweep_diag<KIND, C, false>(wb_a, wl_a, out_a, Wd, ndiag, lane, first_col, pre, Tn, gwait, scr, &s_prog[1], 0);
+        else sweep_diag<KIND, C, true>(wb_a, wl_a, out_a, Wd, ndiag, lane, first_col, pre, Tn, gwait, scr, &s_prog[0], T1 + Wd);
         stamp(beta ? 5 : 4);
     }
     if (MODE == 0) {
@@ -585,8 +627,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
                         bulk_store(g + f, zs, (uint32_t)(min(e - f, (int64_t)piece) * 4), pol);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the zeros have landed ...
-                asm volatile("fence.proxy.async;" ::: "memory");            // ... before anyone patches them
             }
             __syncwarp();
         } else {
@@ -606,6 +646,48 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
             for (int64_t f = a1 + lane; f < f1; f += 32) g[f] = 0.0f;
         }
         stamp(6);
+        // ---- chase: while the zeros drain and the two wavefronts run their last diagonals, the 14 free warps follow
+        // them from the MIDDLE anti-diagonal outwards (alpha has passed it from above, beta from below: the cells of
+        // diagonal e are final once alpha is past e+1 and beta past e+1 from the other side) and replace each staged
+        // log-prob by the exponent's variable part, in the reference's operation order (core.cu:284-294, :319-331):
+        //   WBb[cell] <- (alpha[t,u] + beta[t+1,u]) + lp_blank        WLb[cell] <- (alpha[t,u] + beta[t,u+1]) + lp_label
+        // What is left for after beta[0,0] is known is expf(x - beta00) and the store.
+        if (ok && lw >= 2) {
+            const int CW = kFusedThreads / 32 - 2, cw = lw - 2;
+            const int r0 = t0, r1 = min(t1, Tn);        // rows this CTA patches
+            const int Elast = T1 + U1, mid = Elast >> 1, E0 = T1 + Wd - 1;
+            int pa = 0, pb = 0;                         // cached progress of the alpha / beta wavefront
+            for (int k = cw; k <= Elast && r1 > r0; k += CW) {
+                const int e = (k & 1) ? mid + ((k + 1) >> 1) : mid - (k >> 1);
+                const int ulo = max(0, e - r1 + 1), uhi = min(U1, e - r0);
+                if (ulo > uhi) continue;
+                // alpha: steps <= e+1 done (it reads diagonal e's staged log-probs at step e+1);
+                // beta: anti-diagonal e+1 done = its steps <= E0-e-1, whose operand prefetch covers diagonal e
+                while (pa < e + 2) { pa = flag_acquire(&s_prog[0]); if (pa < e + 2) __nanosleep(100); }
+                while (pb < E0 - e) { pb = flag_acquire(&s_prog[1]); if (pb < E0 - e) __nanosleep(100); }
+                for (int u = ulo + lane; u <= uhi; u += 32) {
+                    const int t = e - u;
+                    const int ib = idxB(t, u);
+                    const float a0v = AL[idxA(t, u)];
+                    const bool last_t = (t == T1), last_u = (u == U1);
+                    if (!(last_t && !last_u)) {
+                        float a = a0v;
+                        if (!last_t) a += BE[ib - Wd];  // beta[t+1,u]: one diagonal earlier, same column
+                        WBb[ib] = a + WBb[ib];
+                    }
+                    if (!last_u) {
+                        const float a = a0v + BE[ib - Wd - 1];   // beta[t,u+1]: previous diagonal, previous primed column
+                        WLb[ib] = a + WLb[ib];
+                    }
+                }
+            }
+            stamp(8);
+        }
+        if (A.tma_fill && lane == 0) {
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the zeros have landed ...
+            asm volatile("fence.proxy.async;" ::: "memory");            // ... before anyone patches them
+        }
+        stamp(9);
     }
     __syncthreads();
 
@@ -615,7 +697,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         if (ok) {
             float b = BE[idxB(0, 0)];                   // beta[0,0]
             if (A.guard) {
-                float a = AL[idxA(T1, U1)] + WBb[idxB(T1, U1)];   // alpha-side ll (core.cu:346)
+                // alpha-side ll = alpha[T-1,U-1] + blank[T-1,U-1] (core.cu:346); MODE 0: the chase has left exactly this sum
+                float a = (MODE == 0 && t0 <= T1 && T1 < t1) ? WBb[idxB(T1, U1)] : AL[idxA(T1, U1)] + WBb[idxB(T1, U1)];
                 if (n == A.poison_n) a += A.poison_delta;              // test hook, see rnnt_b200_debug_guard_poison
                 const float ratio = fabsf(a - b) / fabsf(fmaxf(a, b));
                 if (ratio > 0.001f) {
@@ -631,6 +714,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     }
     if (A.loss_sum && slice == 0 && warp == 0) loss_reduce_last(A.costs, A.scale, A.N, A.loss_sum, A.sync_counter);
     __syncthreads();
+    stamp(10);
     const bool live = ok && !s_bad;
     const float b00 = live ? BE[idxB(0, 0)] : 0.0f;
     const float sc = A.scale ? A.scale[n] : 1.0f;
@@ -660,52 +744,34 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     };
     if (MODE == 0) {
         if (live) {
-            // One ITEM per lane and pass: lane 2k patches the blank gradient and lane 2k+1 the label gradient of
-            // the same cell -- one expf each, and a store instruction covers 16 adjacent cells (the LSU makes one
-            // pass per 128-byte line touched, a cell is 4*V bytes wide).  Four items in flight per thread: all
-            // shared-memory reads and expf chains first, then the stores.
+            // Items (t, u, blank|label) of rows [r0,r1) in row-major order, thread i takes items i, i+512, ...: lanes
+            // (2k,2k+1) = (blank,label) of one cell, a store instruction covers 16 adjacent cells.  The chase has left
+            // x = alpha + beta + lp in the staged planes; here: expf(x - beta00), FastEmit, scale, store.  The item
+            // index walks (row, rest) incrementally -- one division per thread, none per item.
             const int r0 = t0, r1 = min(t1, Tn);
-            const int items = (r1 - r0) * Un * 2;
-            const float inv = 1.0f / (float)Un;
-            const int which = tid & 1;                  // 0 = blank, 1 = label (kFusedThreads is even)
+            const int rows = r1 - r0, per = 2 * Un;
+            const int dq = kFusedThreads / per, dr = kFusedThreads - dq * per;   // both even: the parity of `r` never changes
+            const int which = tid & 1;                  // 0 = blank, 1 = label
             const float *wplane = which ? WLb : WBb;
-            constexpr int G = 4;
-            for (int base = tid; base < items; base += kFusedThreads * G) {
-                float val[G];
-                int64_t off[G];
-                bool go[G];
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const int q = base + g * kFusedThreads;
-                    const bool in = q < items;
-                    const int c = in ? (q >> 1) : 0;
-                    int tt = (int)(((float)c + 0.5f) * inv);
-                    int u = c - tt * Un;
-                    if (u < 0) { --tt; u += Un; } else if (u >= Un) { ++tt; u -= Un; }
-                    const int t = r0 + tt;
-                    const bool last_t = (t == T1), last_u = (u == U1);
-                    const int ib = idxB(t, u);
-                    // same operation order as core.cu:284-294 (blank) and :319-331 (label):
-                    //   blank: a = alpha[t,u] (+ beta[t+1,u] unless last row);  label: a = alpha[t,u] + beta[t,u+1]
-                    const bool add_beta = which ? !last_u : !last_t;
-                    float a = AL[idxA(t, u)];
-                    if (add_beta) a += BE[ib - Wd - which];   // beta[t+1,u]: previous diagonal, same column; beta[t,u+1]: one column before
-                    a = expf(a + wplane[ib] - b00);
+            int tt = tid / per, r = tid - tt * per;
+            while (tt < rows) {
+                const int t = r0 + tt, u = r >> 1;
+                const bool last_t = (t == T1), last_u = (u == U1);
+                const int lab = last_u ? -1 : s_lab[u];
+                // blank: every cell except the last row's inner cells (core.cu:284), and not where the label
+                // store lands on the same element (label == blank: the label gradient wins, core.cu:383-390)
+                const bool go = which ? !last_u : (!(last_t && !last_u) && lab != A.blank);
+                if (go) {
+                    float a = expf(wplane[idxB(t, u)] - b00);
                     // (1. + lambda) * a is a double multiply in the reference (core.cu:327-329); with lambda == 0
                     // it returns a unchanged, so the fp64 round trip is skipped without changing a bit
                     if (which && has_lam) a = (float)((1.0 + (double)A.lam) * (double)a);
                     float v = -a;
                     if (A.scale) v *= sc;
-                    val[g] = v;
-                    const int lab = last_u ? -1 : s_lab[u];
-                    // blank: every cell except the last row's inner cells (core.cu:284), and not where the label
-                    // store lands on the same element (label == blank: the label gradient wins, core.cu:383-390)
-                    go[g] = in && (which ? !last_u : (!(last_t && !last_u) && lab != A.blank));
-                    off[g] = (slab + (int64_t)t * RS + u) * V + (which ? max(lab, 0) : A.blank);
+                    A.grads[(slab + (int64_t)t * RS + u) * V + (which ? lab : A.blank)] = v;
                 }
-#pragma unroll
-                for (int g = 0; g < G; ++g)
-                    if (go[g]) A.grads[off[g]] = val[g];
+                r += dr; tt += dq;
+                if (r >= per) { r -= per; ++tt; }
             }
         }
     } else if (A.pair_grads || A.loc) {
@@ -732,7 +798,7 @@ static long long *g_fused_trace = nullptr;             // diagnostics: see rnnt_
 void set_fused_trace(long long *buf) { g_fused_trace = buf; }
 
 static size_t fused_zero_offset(int T, int U, int Wd, int nd) {
-    const size_t used = sizeof(float) * ((size_t)5 * nd * Wd + (size_t)2 * T) + sizeof(int) * (size_t)U;
+    const size_t used = sizeof(float) * ((size_t)4 * nd * Wd + (size_t)2 * T) + sizeof(int) * (size_t)U;
     return (used + 127) / 128 * 128;
 }
 static size_t fused_smem_bytes(int T, int U, int Wd, int nd) {
@@ -826,17 +892,23 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
     // TMA row gather when a lattice row (U*V floats) is a 16-byte multiple at a 16-byte aligned address and
     // at least four row buffers fit behind the planes (RNNT_B200_GATHER=ldg forces the LDG gather)
     size_t smem = plan.smem;
-    a.nbuf = 0; a.row_off = 0; a.row_stride = 0;
+    a.nbuf = 0; a.row_off = 0; a.row_stride = 0; a.gwn = 0; a.nb_per = 1;
     {
         static const bool want_tma = !env_is("RNNT_B200_GATHER", 'l');
+        static const int nb_env = env_int("RNNT_B200_ROW_BUFS", 0);     // tuning knob: row buffers per gather warp (1 or 2)
         const size_t row = (size_t)U * V * sizeof(float);
         const size_t stride = (row + 127) / 128 * 128;
         // keep two CTAs per SM where the plan counted on them
         const size_t cap = (plan.smem <= 110 * 1024) ? (size_t)113 * 1024 : (size_t)kFusedMaxDynSmem;
         if (want_tma && !pairs_in && (row % 16) == 0 && (reinterpret_cast<uintptr_t>(lp) % 16) == 0 && row <= 32 * 1024 &&
             plan.smem + 4 * stride <= cap) {
-            const int nb = (int)((cap - plan.smem) / stride);
-            a.nbuf = nb < kMaxRowBufs ? nb : kMaxRowBufs;
+            const int fit = (int)((cap - plan.smem) / stride);
+            // two buffers per gather warp once at least 8 fit (the copy of the next row overlaps the picking of this one
+            // and more bytes stay in flight per SM: the gather is bound by that, not by HBM, up to ~20 rows); else one
+            a.nb_per = (nb_env == 1 || nb_env == 2) ? nb_env : (fit >= 8 ? 2 : 1);
+            if (a.nb_per == 2 && fit < 2) a.nb_per = 1;
+            a.gwn = min(kMaxRowBufs, fit / a.nb_per);
+            a.nbuf = a.gwn * a.nb_per;
             a.row_off = (int)(plan.smem);
             a.row_stride = (int)stride;
             smem = plan.smem + (size_t)a.nbuf * stride;
