@@ -141,6 +141,24 @@ int rnnt_b200_gather_backward(void *stream, const float *pair_grads, const int *
                               const float *grad_out, float *out,
                               int N, int T, int U, int V, int blank, int accumulate);
 
+/* Loss straight from un-normalised logits (the reference needs log-softmaxed input, README.md:59, and its
+ * benchmark times F.log_softmax with the loss, pytorch_binding/benchmark.py:65): log_softmax's forward and backward
+ * are fused into the two dense passes this path needs anyway.
+ *   forward : one read of logits (N,T,U,V) -> lse (N,T,U) f32 out [the per-cell normaliser], costs (N), and
+ *             pair_grads (N,T,U,2) out = d cost / d (blank, label) LOG-PROB per cell (NULL = costs only)
+ *   backward: out (N,T,U,V) = d sum_n grad_out[n] cost[n] / d logits
+ *                           = [v==blank] gb + [v==label] gl - exp(logit[v] - lse) (gb + gl), times grad_out[n]
+ *             (grad_out NULL = ones); every element written; a label equal to blank adds both (autograd semantics).
+ * Not bit-identical to torch.log_softmax + the reference (the normaliser is summed in a different order):
+ * costs agree to 1e-5 relative, gradients to 1e-4 absolute (tests/test_gpu_logits.py). */
+int rnnt_b200_logits_forward(void *stream, void *workspace, size_t workspace_bytes, const float *logits,
+                             const int *labels, const int *xn, const int *yn, float *costs, float *lse,
+                             float *pair_grads, int N, int T, int U, int V, int blank, float fastemit_lambda,
+                             int lse_mode);
+int rnnt_b200_logits_backward(void *stream, const float *logits, const float *lse, const float *pair_grads,
+                              const int *labels, const float *grad_out, float *out, int N, int T, int U, int V,
+                              int blank);
+
 /* Compact (ragged) layout.  xs (STU,V), ys (sum yn), STU = sum xn*(yn+1).
  * Replaces run_gather_for_compact + run_warp_rnnt_compact (core.h:41-55) and the host-side
  * prefix sums / .item() syncs of binding.cpp:132-158 (prefix sums are computed on device).

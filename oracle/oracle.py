@@ -204,3 +204,23 @@ def ref_transduce_np_batch(lp, labels, xn, yn, blank=0, fastemit_lambda=0.0):
         costs[n] = c
         grads[n, :Tn, :Un] = g
     return costs, grads
+
+
+# --------------------------------------------------------------------------------------
+# Loss straight from un-normalised logits (the rebuild's fused log_softmax): the oracle composes
+# the reference's own two steps in fp64 -- log_softmax (benchmark.py:65) then the loss -- and differentiates through
+# both: d/d logit[v] = g_lp[v] - softmax[v] * sum_v' g_lp[v'].
+# --------------------------------------------------------------------------------------
+def from_logits(logits, labels, xn, yn, blank=0, fastemit_lambda=0.0, grad_output=None):
+    """-> (costs (N,), d sum_n grad_output[n]*cost[n] / d logits (N,T,U,V)), fp64."""
+    x = np.asarray(logits, dtype=np.float64)
+    m = x.max(axis=-1, keepdims=True)
+    lse = m + np.log(np.exp(x - m).sum(axis=-1, keepdims=True))
+    lp = x - lse
+    costs, g = dense(lp, labels, xn, yn, blank, fastemit_lambda)
+    # a label equal to blank: dense() overrides (core.cu's launch order); autograd through log_softmax ADDS.  The
+    # inputs of the tests avoid that case, as the reference's benchmark recipe does (labels in [1, V)).
+    gl = g - np.exp(lp) * g.sum(axis=-1, keepdims=True)
+    if grad_output is not None:
+        gl = gl * np.asarray(grad_output, dtype=np.float64).reshape(-1, 1, 1, 1)
+    return costs, gl

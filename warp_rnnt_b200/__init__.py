@@ -130,6 +130,50 @@ class RNNTLossGather(torch.autograd.Function):
         return g, None, None, None, None, None
 
 
+class RNNTLossFromLogits(torch.autograd.Function):
+    """Loss straight from un-normalised joint-network logits: ``log_softmax`` fused into the loss.
+
+    The reference needs log-softmaxed input (README.md:59; its benchmark times ``F.log_softmax`` with the loss,
+    benchmark.py:65): seven dense passes over (N,T,U,V) per step.  Here forward reads the logits once (per-cell
+    normaliser + the two log-probs the recurrence needs) and keeps a (N,T,U,2) gradient; backward reads them once more
+    and writes d loss / d LOGITS, applying log_softmax's backward on the fly: three dense passes."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, frames_lengths, labels_lengths, blank=0, fastemit_lambda=0.0):
+        need = ctx.needs_input_grad[0]
+        costs, lse, pg = _C.rnnt_logits_forward(logits, labels, frames_lengths, labels_lengths, blank,
+                                                fastemit_lambda, need, 0)
+        if need:
+            ctx.save_for_backward(logits, lse, pg, labels)
+            ctx.blank = blank
+        return costs
+
+    @staticmethod
+    def backward(ctx, grads_output):
+        logits, lse, pg, labels = ctx.saved_tensors
+        go = grads_output.contiguous().to(torch.float32)
+        return _C.rnnt_logits_backward(logits, lse, pg, labels, go, ctx.blank), None, None, None, None, None
+
+
+def rnnt_loss_from_logits(logits, labels, frames_lengths, labels_lengths, average_frames=False, reduction="none",
+                          blank=0, fastemit_lambda=0.0):
+    """``rnnt_loss(log_softmax(logits, -1), ...)`` in three dense passes instead of seven; the gradient is w.r.t. the
+    LOGITS.  Dense (N,T,U,V) float32 layout; other arguments as in ``rnnt_loss``.  Agrees with
+    ``torch.log_softmax`` + the reference to 1e-5 (costs, relative) / 1e-4 (gradients), not bit for bit."""
+    assert average_frames is None or isinstance(average_frames, bool)
+    assert reduction is None or reduction in ("none", "mean", "sum")
+    assert isinstance(blank, int)
+    assert not labels.requires_grad and not frames_lengths.requires_grad and not labels_lengths.requires_grad
+    costs = RNNTLossFromLogits.apply(logits, labels, frames_lengths, labels_lengths, blank, fastemit_lambda)
+    if average_frames:
+        costs = costs / frames_lengths.to(logits)
+    if reduction == "sum":
+        return costs.sum()
+    if reduction == "mean":
+        return costs.mean()
+    return costs
+
+
 class RNNTLossEager(torch.autograd.Function):
     """Reference-shaped variant: dense gradients are produced in forward (one fused pass) and
     scaled in backward, exactly like the reference's RNNTLoss (__init__.py:11-24)."""
@@ -251,5 +295,5 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=
             f"Unknown reduction method: {reduction}, expected to be one of ['mean', 'sum', 'none']")
 
 
-__all__ = ["rnnt_loss", "RNNTLoss", "RNNTLossGather", "RNNTLossEager", "RNNTLossCompact", "compact_hints", "set_lse_mode", "core", "_C",
+__all__ = ["rnnt_loss", "rnnt_loss_from_logits", "RNNTLossFromLogits", "RNNTLoss", "RNNTLossGather", "RNNTLossEager", "RNNTLossCompact", "compact_hints", "set_lse_mode", "core", "_C",
            "__version__"]

@@ -265,6 +265,55 @@ std::tuple<at::Tensor, at::Tensor> rnnt_gather_forward(const at::Tensor &xs, con
     return std::make_tuple(costs, pg);
 }
 
+// loss from un-normalised logits: (costs (N), lse (N,T,U), pair_grads (N,T,U,2) or empty)
+std::tuple<at::Tensor, at::Tensor, at::Tensor> rnnt_logits_forward(const at::Tensor &xs, const at::Tensor &ys,
+                                                                   const at::Tensor &xn, const at::Tensor &yn,
+                                                                   int blank, float fastemit_lambda, bool want_grads,
+                                                                   int lse_mode) {
+    check4(xs, ys, xn, yn);
+    check_dense_shapes(xs, ys, xn, yn);
+    const c10::cuda::CUDAGuard guard(xs.device());
+    const int64_t N = xs.size(0), T = xs.size(1), U = xs.size(2), V = xs.size(3);
+    TORCH_CHECK(blank >= 0 && blank < V, "blank must be in [0, V)");
+    at::Tensor costs = at::empty({N}, xs.options());
+    at::Tensor lse = at::empty({N, T, U}, xs.options());
+    at::Tensor pg = want_grads ? at::empty({N, T, U, 2}, xs.options()) : at::empty({0}, xs.options());
+    if (N == 0) return std::make_tuple(costs, lse, pg);
+    at::Tensor ws = workspace_for(xs, N * T * U, N);
+    check_status(rnnt_b200_logits_forward(current_stream(xs), ws.data_ptr(), (size_t)ws.numel(), xs.data_ptr<float>(),
+                                          ys.data_ptr<int>(), xn.data_ptr<int>(), yn.data_ptr<int>(),
+                                          costs.data_ptr<float>(), lse.data_ptr<float>(),
+                                          want_grads ? pg.data_ptr<float>() : nullptr, (int)N, (int)T, (int)U, (int)V,
+                                          blank, fastemit_lambda, lse_mode));
+    return std::make_tuple(costs, lse, pg);
+}
+
+at::Tensor rnnt_logits_backward(const at::Tensor &xs, const at::Tensor &lse, const at::Tensor &pair_grads,
+                                const at::Tensor &ys, const at::Tensor &grad_out, int blank) {
+    TORCH_CHECK(xs.is_contiguous() && xs.scalar_type() == at::ScalarType::Float && xs.device().is_cuda() && xs.dim() == 4,
+                "xs must be a contiguous CUDA Float tensor of shape (N, T, U, V)");
+    const int64_t N = xs.size(0), T = xs.size(1), U = xs.size(2), V = xs.size(3);
+    TORCH_CHECK(lse.is_contiguous() && lse.scalar_type() == at::ScalarType::Float && lse.device() == xs.device() &&
+                    lse.numel() == N * T * U,
+                "lse must be a contiguous Float tensor of shape (N, T, U) on the device of xs");
+    TORCH_CHECK(pair_grads.is_contiguous() && pair_grads.scalar_type() == at::ScalarType::Float &&
+                    pair_grads.device() == xs.device() && pair_grads.numel() == N * T * U * 2,
+                "pair_grads must be a contiguous Float tensor of shape (N, T, U, 2) on the device of xs");
+    TORCH_CHECK(ys.is_contiguous() && ys.scalar_type() == at::ScalarType::Int && ys.device() == xs.device() &&
+                    ys.dim() == 2 && ys.size(0) == N && ys.size(1) + 1 == U,
+                "ys must be a contiguous Int tensor of shape (N, U-1) on the device of xs");
+    TORCH_CHECK(grad_out.is_contiguous() && grad_out.scalar_type() == at::ScalarType::Float &&
+                    grad_out.device() == xs.device() && grad_out.numel() == N,
+                "grad_out must be a contiguous Float tensor of shape (N,)");
+    TORCH_CHECK(blank >= 0 && blank < V, "blank must be in [0, V)");
+    const c10::cuda::CUDAGuard guard(xs.device());
+    at::Tensor out = at::empty_like(xs);
+    check_status(rnnt_b200_logits_backward(current_stream(xs), xs.data_ptr<float>(), lse.data_ptr<float>(),
+                                           pair_grads.data_ptr<float>(), ys.data_ptr<int>(), grad_out.data_ptr<float>(),
+                                           out.data_ptr<float>(), (int)N, (int)T, (int)U, (int)V, blank));
+    return out;
+}
+
 at::Tensor rnnt_gather_backward(const at::Tensor &pair_grads, const at::Tensor &ys, const at::Tensor &grad_out,
                                 int64_t V, int blank, bool accumulate) {
     TORCH_CHECK(pair_grads.is_contiguous() && pair_grads.scalar_type() == at::ScalarType::Float &&
@@ -305,6 +354,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("blank") = 0, py::arg("fastemit_lambda") = 0.0, py::arg("grad_scale") = py::none(),
           py::arg("want_grads") = true, py::arg("lse_mode") = 0);
     m.def("rnnt_rescale_", &rnnt_rescale_, py::arg("grads"), py::arg("grad_out"), py::arg("applied") = py::none());
+    m.def("rnnt_logits_forward", &rnnt_logits_forward, py::arg("xs"), py::arg("ys"), py::arg("xn"), py::arg("yn"),
+          py::arg("blank") = 0, py::arg("fastemit_lambda") = 0.0, py::arg("want_grads") = true, py::arg("lse_mode") = 0);
+    m.def("rnnt_logits_backward", &rnnt_logits_backward, py::arg("xs"), py::arg("lse"), py::arg("pair_grads"),
+          py::arg("ys"), py::arg("grad_out"), py::arg("blank") = 0);
     m.def("rnnt_gather_forward", &rnnt_gather_forward, py::arg("xs"), py::arg("ys"), py::arg("xn"), py::arg("yn"),
           py::arg("blank") = 0, py::arg("fastemit_lambda") = 0.0, py::arg("want_grads") = true,
           py::arg("lse_mode") = 0);

@@ -29,6 +29,7 @@
 // grid (S, N): S CTAs per lattice recompute the (cheap) wavefront redundantly and split the
 // (bandwidth-bound) fill/patch of the lattice's rows, so small batches still use every SM.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -221,6 +222,8 @@ struct FusedArgs {
     int nd;                 // staged rows (diagonals) allocated = T + Wd + 16
     int gw;                 // warps that gather (of the 14 non-wavefront warps); MODE 0: the rest start the zero-fill at once
     int tma_fill;           // MODE 0: zero-fill with bulk shared->global copies (else 256-bit STG)
+    int fill_warps;         // MODE 0, bulk fill: how many of the 14 free warps issue it (the others chase at once)
+    int debug;              // bit 0: skip the patch stores (timing experiments only; results are wrong)
     long long *trace;       // optional per-CTA phase stamps (clock64), 8 per CTA; null = off
     float *loss_sum;        // optional: sum_n costs[n] * (scale ? scale[n] : 1), written by the last CTA to finish
     unsigned *sync_counter; // with loss_sum: device counter, 0 on entry, left 0 (self-resetting)
@@ -614,7 +617,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         constexpr int kChunk = 8192;                    // floats per chunk
         const int64_t nfill = (a1 - a0 + kChunk - 1) / kChunk;
         if (A.tma_fill) {
-            if (lane == 0) {
+            // the bulk-copy issue blocks when the SM's copy queue is full (the zeros drain at HBM speed), so only
+            // `fill_warps` warps issue -- one instruction per 8 KB keeps the queue full -- and the others chase at once
+            if (lane == 0 && (lw < 2 || lw >= 2 + (kFusedThreads / 32 - 2) - A.fill_warps)) {
                 const uint64_t pol = policy_evict_last();
                 const uint32_t zs = (uint32_t)__cvta_generic_to_shared(zbuf);
                 constexpr int piece = kZeroBytes / 4;   // floats per bulk copy
@@ -754,25 +759,37 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
             const int which = tid & 1;                  // 0 = blank, 1 = label
             const float *wplane = which ? WLb : WBb;
             int tt = tid / per, r = tid - tt * per;
-            while (tt < rows) {
-                const int t = r0 + tt, u = r >> 1;
-                const bool last_t = (t == T1), last_u = (u == U1);
-                const int lab = last_u ? -1 : s_lab[u];
-                // blank: every cell except the last row's inner cells (core.cu:284), and not where the label
-                // store lands on the same element (label == blank: the label gradient wins, core.cu:383-390)
-                const bool go = which ? !last_u : (!(last_t && !last_u) && lab != A.blank);
-                if (go) {
-                    float a = expf(wplane[idxB(t, u)] - b00);
-                    // (1. + lambda) * a is a double multiply in the reference (core.cu:327-329); with lambda == 0
-                    // it returns a unchanged, so the fp64 round trip is skipped without changing a bit
-                    if (which && has_lam) a = (float)((1.0 + (double)A.lam) * (double)a);
-                    float v = -a;
-                    if (A.scale) v *= sc;
-                    A.grads[(slab + (int64_t)t * RS + u) * V + (which ? lab : A.blank)] = v;
+            // running staged index and output offset of the item: a pass moves dq rows down and dr/2 columns right,
+            // a wrap (r >= per) one more row down and Un columns back
+            int ib = idxB(r0 + tt, r >> 1);
+            const int dib = -dq * Wd - (dr >> 1) * (Wd + 1), wib = -Wd + Un * (Wd + 1);
+            int64_t off = (slab + (int64_t)(r0 + tt) * RS + (r >> 1)) * V;
+            const int64_t doff = ((int64_t)dq * RS + (dr >> 1)) * V, woff = (int64_t)(RS - Un) * V;
+            float *const g = A.grads;
+            const double lam1 = 1.0 + (double)A.lam;
+            auto patch = [&](auto with_lam) {
+                while (tt < rows) {
+                    const int u = r >> 1;
+                    const bool last_t = (r0 + tt == T1), last_u = (u == U1);
+                    const int lab = last_u ? -1 : s_lab[u];
+                    // blank: every cell except the last row's inner cells (core.cu:284), and not where the label
+                    // store lands on the same element (label == blank: the label gradient wins, core.cu:383-390)
+                    const bool go = which ? !last_u : (!(last_t && !last_u) && lab != A.blank);
+                    if (go) {
+                        float a = expf(wplane[ib] - b00);
+                        // (1. + lambda) * a is a double multiply in the reference (core.cu:327-329); with lambda == 0
+                        // it returns a unchanged, so the fp64 round trip is skipped without changing a bit
+                        if (decltype(with_lam)::value && which) a = (float)(lam1 * (double)a);
+                        float v = -a;
+                        if (A.scale) v *= sc;
+                        if (!(A.debug & 1)) g[off + (which ? lab : A.blank)] = v;
+                        else if (v == 123.25f) A.costs[n] = v;
+                    }
+                    r += dr; tt += dq; ib += dib; off += doff;
+                    if (r >= per) { r -= per; ++tt; ib += wib; off += woff; }
                 }
-                r += dr; tt += dq;
-                if (r >= per) { r -= per; ++tt; }
-            }
+            };
+            if (has_lam) patch(std::true_type{}); else patch(std::false_type{});
         }
     } else if (A.pair_grads || A.loc) {
         // dense: every cell of rows [t0,t1) incl. padding (zeros); compact: the packed cells of rows < Tn
@@ -917,6 +934,10 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
     {
         static const bool tma = !env_is("RNNT_B200_FILL", 's');   // RNNT_B200_FILL=stg selects the 256-bit store fill
         a.tma_fill = tma ? 1 : 0;
+        static const int fw = env_int("RNNT_B200_FILL_WARPS", 2);
+        a.fill_warps = max(1, min(fw, kFusedThreads / 32 - 2));
+        static const int dbg = env_int("RNNT_B200_DEBUG", 0);
+        a.debug = dbg;
     }
     a.trace = g_fused_trace;
     { const GuardPoison gp = guard_poison(); a.poison_n = gp.n; a.poison_delta = gp.delta; }

@@ -40,6 +40,12 @@ struct ExpandSrc {
 cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src, float *out, int64_t cells,
                           int V, int blank, bool retire_early = false);
 
+// logits.cu -- loss from un-normalised logits (fused log_softmax forward / backward)
+cudaError_t launch_lse_pairs(cudaStream_t s, const float *x, const int *labels, int N, int T, int U, int V, int blank,
+                             float2 *pairs, float *lse);
+cudaError_t launch_expand_logits(cudaStream_t s, const float *x, const float *lse, const float2 *pg, const int *labels,
+                                 const float *grad_out, float *out, int N, int T, int U, int V, int blank);
+
 // fused.cu -- single-kernel path for lattices that fit shared memory
 struct FusedPlan { int W, ring, nw, slices; size_t smem; };
 bool fused_plan(int N, int T, int U, FusedPlan *plan);
