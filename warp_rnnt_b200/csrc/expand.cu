@@ -90,34 +90,31 @@ template <int MODE>
 __global__ void __launch_bounds__(kExpandThreads)
 k_expand(Problem p, ExpandSrc src, float *__restrict__ out, int64_t cells, int V, int blank, int rows_per_chunk,
          FastDiv divV, FastDiv divU, FastDiv divTU, int vec_ok) {
-    // staged per output row: (blank grad, label grad, label id or -1, -)
-    __shared__ __align__(16) float4 s_row[kExpandMaxRows + 1];
+    __shared__ float2 s_g[kExpandMaxRows];
+    __shared__ int s_lab[kExpandMaxRows];
     const int64_t nchunks = (cells + rows_per_chunk - 1) / rows_per_chunk;
-    const bool adds = (MODE == 1) && src.label_adds;
-    // the thread's vector advances by 4*kExpandThreads floats per pass: (rows, floats) of that stride, once
-    const uint32_t stride_rows = divV.div(4u * kExpandThreads), stride_v = 4u * kExpandThreads - stride_rows * (uint32_t)V;
     for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         const int64_t r0 = chunk * rows_per_chunk;
         const int rows = (int)min((int64_t)rows_per_chunk, cells - r0);
-        __syncthreads();  // previous chunk's sweep is done with s_row
+        __syncthreads();  // previous chunk's sweep is done with s_g / s_lab
         // ---- phase 1: stage the rows' non-zeros
         for (int r = threadIdx.x; r < rows; r += kExpandThreads) {
             float2 g;
             int lab;
             stage_row<MODE>(p, src, r0 + r, blank, divU, divTU, g, lab);
-            // override mode: a zero label gradient marks "no label transition here" (padded labels may equal blank)
-            if (MODE == 1 && !adds && g.y == 0.0f) lab = -1;
-            s_row[r] = make_float4(g.x, g.y, __int_as_float(lab), 0.0f);
+            s_g[r] = g;
+            s_lab[r] = lab;
         }
-        if (threadIdx.x == 0) s_row[rows] = make_float4(0.0f, 0.0f, __int_as_float(-1), 0.0f);   // read, never used
         __syncthreads();
         // ---- phase 2: sweep the chunk's floats [f0, f1)
         const int64_t f0 = r0 * (int64_t)V;
         const int64_t f1 = f0 + (int64_t)rows * V;
         auto value = [&](int row, int v) -> float {
-            const float4 q = s_row[row];
-            float x = (v == blank) ? q.x : 0.0f;
-            if (v == __float_as_int(q.z)) x = adds ? x + q.y : q.y;
+            const float2 g = s_g[row];
+            const int lab = s_lab[row];
+            float x = (v == blank) ? g.x : 0.0f;
+            // override mode: a zero label gradient marks "no label transition here" (padded labels may equal blank)
+            if (v == lab) x = (MODE == 1 && src.label_adds) ? x + g.y : ((MODE == 1 && g.y == 0.0f) ? x : g.y);
             return x;
         };
         int64_t a0 = vec_ok ? min(f1, (f0 + 3) & ~(int64_t)3) : f1;
@@ -133,52 +130,36 @@ k_expand(Problem p, ExpandSrc src, float *__restrict__ out, int64_t cells, int V
             const uint32_t row = divV.div(local);
             st_cs(out + f, value((int)row, (int)(local - row * V)));
         }
-        int64_t f = a0 + 4 * (int64_t)threadIdx.x;
-        if (f < a1) {
-            // (row, v) of the vector's first float: one division here, then a running cursor
-            uint32_t row = divV.div((uint32_t)(f - f0));
-            int v = (int)((uint32_t)(f - f0) - row * V);
-            for (; f < a1; f += 4 * kExpandThreads) {
-                float e[4];
-                if ((V & 3) == 0) {
-                    // rows are whole vectors: one staged-row fetch, four compare/selects
-                    const float4 q = s_row[row];
-                    const int pb = blank - v, pl = __float_as_int(q.z) - v;
+        for (int64_t f = a0 + 4 * (int64_t)threadIdx.x; f < a1; f += 4 * kExpandThreads) {
+            const uint32_t local = (uint32_t)(f - f0);
+            uint32_t row = divV.div(local);
+            int v = (int)(local - row * V);
+            float e[4];
+            if ((V & 3) == 0) {
+                // rows are whole vectors: one staged-row fetch, four compare/selects.  (Kernel-uniform
+                // test on purpose: a per-vector "does it straddle a row end" branch makes nearly every
+                // warp run both paths -- measured 15 % slower at V = 50.  Also tried and dropped: composing
+                // 16 KB tiles in shared memory and streaming them out, 40 % slower at V = 50 because the
+                // per-chunk barriers and staging latency are amortised over too few bytes.)
+                const float2 g = s_g[row];
+                const int lab = s_lab[row];
+                const int pb = blank - v, pl = lab - v;
+                const bool adds = (MODE == 1) && src.label_adds;
+                const bool lab_live = (MODE != 1) || adds || (g.y != 0.0f);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float x = (k == pb) ? q.x : 0.0f;
-                        if (k == pl) x = adds ? x + q.y : q.y;
-                        e[k] = x;
-                    }
-                } else if (V >= 4) {
-                    // a vector touches this row and at most the next one: fetch both, select per element -- no
-                    // per-vector branch (most warps would run both sides), no division, no second staged-row fetch
-                    // per float.  (Tried and dropped: composing 16 KB tiles in shared memory and streaming them out,
-                    // 40 % slower at V = 50 because the per-chunk barriers are amortised over too few bytes.)
-                    const float4 q0 = s_row[row], q1 = s_row[row + 1];
-                    const int l0 = __float_as_int(q0.z), l1 = __float_as_int(q1.z);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const bool nx = v + k >= V;
-                        const int vv = nx ? v + k - V : v + k;
-                        const float gb = nx ? q1.x : q0.x, gl = nx ? q1.y : q0.y;
-                        float x = (vv == blank) ? gb : 0.0f;
-                        if (vv == (nx ? l1 : l0)) x = adds ? x + gl : gl;
-                        e[k] = x;
-                    }
-                } else {
-                    int rr = (int)row, vv = v;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        e[k] = value(rr, vv);
-                        if (++vv == V) { vv = 0; ++rr; }
-                    }
+                for (int k = 0; k < 4; ++k) {
+                    float x = (k == pb) ? g.x : 0.0f;
+                    if (k == pl && lab_live) x = adds ? x + g.y : g.y;
+                    e[k] = x;
                 }
-                st_cs_v4(out + f, make_float4(e[0], e[1], e[2], e[3]));
-                v += (int)stride_v;
-                row += stride_rows;
-                if (v >= V) { v -= V; ++row; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    e[k] = value((int)row, v);
+                    if (++v == V) { v = 0; ++row; }
+                }
             }
+            st_cs_v4(out + f, make_float4(e[0], e[1], e[2], e[3]));
         }
     }
 }

@@ -213,11 +213,6 @@ struct Sweep {
 // producing inf - inf.
 constexpr float kBig = -1.0e30f;
 
-// (wb, wl) = (0, kBig) in global memory: where the steady-state loop of sweep_warp points the operand loads of lanes
-// that have nothing to load (columns past the lattice, the first column's missing label edge), so that its loads
-// need no predicates.
-__device__ const float g_sentinel[2] = {0.0f, kBig};
-
 // One direction of one lattice.  "Primed" coordinates (i,j): alpha uses (t,u); beta uses
 // (Tn-1-t, Un-1-u), so both are the same recurrence
 //   val[i,j] = LSE(val[i-1,j] + wB(i,j), val[i,j-1] + wL(i,j)),  val[0,0] = init
@@ -290,52 +285,7 @@ __device__ __forceinline__ float sweep_warp(const Sweep &S) {
     for (int k = 0; k < kPrefetch; ++k) fetch(k, k);
 
     float *op = S.o + c0;
-    // Steady state: a block of kPrefetch steps in which every lane's row -- for the step itself and for the operands it
-    // prefetches kPrefetch steps ahead -- lies inside the lattice.  There the loads need no row predicates, the store
-    // and ring tests are loop-invariant, and the addresses advance by pointer increments: ~65 instructions per step
-    // instead of ~150 in the general block (which handles the ramp-up / ramp-down triangles at both ends).
-    const float *base_wb = reinterpret_cast<const float *>(S.pr + c0) - (BETA ? 0 : 2 * (int64_t)st);
-    const float *base_wl = reinterpret_cast<const float *>(S.pr + c0) + (BETA ? 1 : -1);
-    const bool lane_ok = S.col_ok;
-    const bool wl_ok = lane_ok && !first_col;
-    const int64_t dsb = lane_ok ? 2 * ds : 0, dsl = wl_ok ? 2 * ds : 0, dsm = mem_lane ? ds : 0;
     for (int s0 = 0; s0 < S.nsteps; s0 += kPrefetch) {
-        if (s0 >= 32 && s0 + 2 * kPrefetch <= Tn) {
-            const float *pwb = lane_ok ? base_wb + (int64_t)(s0 + kPrefetch) * dsb : g_sentinel;
-            const float *pwl = wl_ok ? base_wl + (int64_t)(s0 + kPrefetch) * dsl : g_sentinel + 1;
-            const float *pbd = mem_lane ? S.o + c0 + (int64_t)(s0 + kPrefetch) * ds + bcol : g_sentinel;
-#pragma unroll
-            for (int k = 0; k < kPrefetch; ++k) {
-                const int s = s0 + k;
-                float left = __shfl_up_sync(0xffffffffu, val, 1);
-                if (SRC == kLeftRing) {
-                    const float b = ring_get(s);
-                    if (lane == 0) left = b;
-                } else if (SRC == kLeftMem) {
-                    if (lane == 0) left = bnd[k];
-                }
-                float v = lse<KIND>(val + wb[k], left + wl[k]);
-                if (SRC == kLeftMem) {
-                    if (S.override0 && lane == 0) v = bnd[k];      // column 0 from the scan pre-pass
-                }
-                val = v;
-                if (lane_ok) {
-                    *op = v;
-                    last = v;
-                }
-                op += ds;
-                if (S.publish) ring_put(s - 31, v);
-                wb[k] = __ldg(pwb);
-                wl[k] = __ldg(pwl);
-                pwb += dsb;
-                pwl += dsl;
-                if (SRC == kLeftMem) {
-                    bnd[k] = __ldcg(pbd);
-                    pbd += dsm;
-                }
-            }
-            continue;
-        }
 #pragma unroll
         for (int k = 0; k < kPrefetch; ++k) {
             const int s = s0 + k;                               // steps past nsteps are harmless no-ops
