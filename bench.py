@@ -51,17 +51,31 @@ WORKLOADS = {
     "c4d": (64, 1500, 300, 50, "dense", False, "N=64 T=1500 U=300 V=50 dense layout, full lengths (variant of configs[3])"),
     "c5mb": (32, 600, 150, 1024, "dense", False,
              "N=32 T=600 U=150 V=1024 = one micro-batch of BASELINE configs[4] (256 lattices/GPU as 8 x 32)"),
+    # next rows: bf16 I/O and the loss straight from logits -- reported BESIDE the f32 headline
+    "c2b": (128, 150, 40, 28, "bf16", False, "N=128 T=150 U=40 V=28, bfloat16 log_probs in / bfloat16 gradient out"),
+    "c5mbb": (64, 600, 150, 1024, "bf16", False,
+              "N=64 T=600 U=150 V=1024 bfloat16 i/o = a double-size micro-batch of BASELINE configs[4]"),
+    "c2l": (128, 150, 40, 28, "logits", False,
+            "N=128 T=150 U=40 V=28 from un-normalised logits (log_softmax fused; gradient w.r.t. logits)"),
 }
 API_CALL = {"dense": "warp_rnnt_b200.rnnt_loss(x, ..., reduction='sum').backward()",
             "gather": "warp_rnnt_b200.rnnt_loss(x, ..., reduction='sum', gather=True).backward()",
-            "compact": "warp_rnnt_b200.rnnt_loss(x, ..., reduction='sum', compact=True).backward() inside compact_hints(T, U)"}
+            "compact": "warp_rnnt_b200.rnnt_loss(x, ..., reduction='sum', compact=True).backward() inside compact_hints(T, U)",
+            "bf16": "warp_rnnt_b200.rnnt_loss(x_bf16, ..., reduction='sum').backward()",
+            "logits": "warp_rnnt_b200.rnnt_loss_from_logits(logits, ..., reduction='sum').backward()"}
 
 
-def b_alg(N, T, U, V, cells=None):
+def b_alg(N, T, U, V, cells=None, mode="dense"):
     """dense gradient write + the two log-probs per cell + labels + lengths/costs.  Ragged layouts:
-    `cells` = sum xn*(yn+1) replaces N*T*U."""
+    `cells` = sum xn*(yn+1) replaces N*T*U.  bf16 i/o: 2-byte elements.  from logits: the whole tensor must be read
+    (the normaliser needs every logit) and the gradient is dense: 8 bytes per element."""
     c = N * T * U if cells is None else cells
-    return 4 * c * V + 8 * c + 4 * N * (U - 1) + 12 * N
+    small = 4 * N * (U - 1) + 12 * N
+    if mode == "bf16":
+        return 2 * c * V + 4 * c + small
+    if mode == "logits":
+        return 8 * c * V + small
+    return 4 * c * V + 8 * c + small
 
 
 def peaks():
@@ -74,7 +88,7 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_host_inputs(N, T, U, V, seed, ragged=False, compact=False):
+def make_host_inputs(N, T, U, V, seed, ragged=False, compact=False, dtype=None):
     """The reference's recipe (pytorch_binding/benchmark.py:11-27): randn -> log_softmax, labels in [1,V), full
     lengths; ragged = the random-length recipe of benchmark2.py:81-85 (lengths in [T/2,T] / [U/2,U), shifted so the
     maxima hit T / U-1); compact = the ragged concat of test.py:291-299.  Pinned host tensors."""
@@ -94,6 +108,8 @@ def make_host_inputs(N, T, U, V, seed, ragged=False, compact=False):
         ys = torch.cat([ys[i, :yn[i]] for i in range(N)]).contiguous()
     else:
         xs = torch.log_softmax(torch.randn((N, T, U, V), dtype=torch.float32, generator=g), dim=-1)
+    if dtype is not None:
+        xs = xs.to(dtype)
     pin = torch.cuda.is_available()
     return tuple(t.pin_memory() if pin else t for t in (xs, ys, xn, yn))
 
@@ -185,8 +201,9 @@ def rotation(per_set_bytes):
     return int(max(2, min(6, (700e6 // per_set_bytes) + 1))) if per_set_bytes < 4e9 else 1
 
 
-def timed(fn, steps, world, dist, dev):
-    """CUDA events around exactly `steps` calls, barrier + synchronize on both sides, max over ranks -> ms."""
+def timed(fn, steps, world, dist, dev, after=None):
+    """CUDA events around exactly `steps` calls (+ `after()`, e.g. waiting for the last in-flight all-reduce), barrier +
+    synchronize on both sides, max over ranks -> ms."""
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -195,6 +212,8 @@ def timed(fn, steps, world, dist, dev):
     e0.record()
     for i in range(steps):
         fn(i)
+    if after is not None:
+        after()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -243,9 +262,11 @@ def main():
     w.set_lse_mode(args.lse)
 
     # R rotating input sets, R live outputs: no step re-touches lines of the previous ones
-    per_set = 2 * 4 * N * T * U * V
+    esz = 2 if mode == "bf16" else 4
+    per_set = 2 * esz * N * T * U * V
     R = rotation(per_set)
-    host = [make_host_inputs(N, T, U, V, seed=1000 * rank + N + i, ragged=ragged, compact=(mode == "compact"))
+    host = [make_host_inputs(N, T, U, V, seed=1000 * rank + N + i, ragged=ragged, compact=(mode == "compact"),
+                             dtype=torch.bfloat16 if mode == "bf16" else None)
             for i in range(R)]
     sets = [tuple(t.to(dev, non_blocking=True) for t in h) for h in host]
     cells = [int((h[2].long() * (h[3].long() + 1)).sum()) for h in host]
@@ -253,28 +274,41 @@ def main():
         s[0].requires_grad_(True)
     torch.cuda.synchronize()
 
-    # ---- the step = what a user of the reference's API calls (loss + gradient w.r.t. log_probs)
+    # ---- the step = what a user of the reference's API calls (loss + gradient w.r.t. log_probs).  N > 1: every rank
+    # runs it on its own shard; the gradients need only the LOCAL loss (the weights are known up front), so the one
+    # collective -- the scalar all-reduce -- is issued asynchronously after the step and overlaps the next one
+    # (parallel.all_reduce_loss_async); it is waited for one step later, inside the timed region.
     def api_step(s):
         x, ys, xn, yn = s
         x.grad = None
-        if world > 1:
-            ctx = w.compact_hints(T, U) if mode == "compact" else contextlib.nullcontext()
-            with ctx:
-                loss = parallel.rnnt_loss_sharded(x, ys, xn, yn, reduction="sum", gather=(mode == "gather"),
-                                                  compact=(mode == "compact"))
-        elif mode == "compact":
+        if mode == "compact":
             with w.compact_hints(T, U):                 # sync-free forward (no D2H shape validation)
                 loss = w.rnnt_loss(x, ys, xn, yn, reduction="sum", compact=True)
+        elif mode == "logits":
+            loss = w.rnnt_loss_from_logits(x, ys, xn, yn, reduction="sum")
         else:
             loss = w.rnnt_loss(x, ys, xn, yn, reduction="sum", gather=(mode == "gather"))
         loss.backward()
         return loss
 
+    pending = []
+
+    def reduce_async(loss):
+        if world > 1:
+            pending.append(parallel.all_reduce_loss_async(loss.detach()))
+            if len(pending) > 1:
+                pending.pop(0).wait()
+
+    def drain():
+        while pending:
+            pending.pop(0).wait()
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     # eager warm-up on every set: primes the caching allocator, NCCL and the lazy per-device state
     for i in range(R + 2):
-        api_step(sets[i % R])
+        reduce_async(api_step(sets[i % R]))
+    drain()
     torch.cuda.synchronize()
 
     # ---- CUDA graphs of the API step, one per input set (kills the python / autograd dispatch time, which at cfg 2
@@ -305,15 +339,18 @@ def main():
 
     if graphs is not None:
         def step(i):
-            graphs[i % R][0].replay()
+            g, loss, _ = graphs[i % R]
+            g.replay()
+            reduce_async(loss)
     else:
         def step(i):
-            api_step(sets[i % R])
+            reduce_async(api_step(sets[i % R]))
 
     for i in range(args.warmup):
         step(i)
+    drain()
     n0 = w._C.launch_count()
-    ms = timed(lambda i: step(args.warmup + i), args.steps, world, dist, dev)
+    ms = timed(lambda i: step(args.warmup + i), args.steps, world, dist, dev, after=drain)
     launches = (launches_per_step * args.steps) if graphs is not None else int(w._C.launch_count() - n0)
     ms_per_step = ms / args.steps
     value = N * world * args.steps / (ms * 1e-3)
@@ -366,6 +403,8 @@ def main():
                 for dst, src in zip(s, h):
                     dst.copy_(src, non_blocking=True)
             loss = api_step(s)
+        if world > 1:                                   # the value is read right away: blocking all-reduce
+            dist.all_reduce(loss.detach())
         return float(loss.item())                       # D2H read of the step's result
 
     for i in range(2):
@@ -393,26 +432,34 @@ def main():
         c5 = run_c5(w, parallel, dist, dev, world, rank)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world, dist)
         return
     peak, peak_src = peaks()
-    balg = b_alg(N, T, U, V, cells=sum(cells) / len(cells) if mode == "compact" or ragged else None)
-    achieved = balg / (ms_per_step * 1e-3) / 1e9
+    balg = b_alg(N, T, U, V, cells=sum(cells) / len(cells) if mode == "compact" or ragged else None, mode=mode)
+    # roofline of the DOMINANT KERNEL: on the dense f32 path that is the one kernel of the operator call (CUDA events
+    # around back-to-back launches); the API step adds the rescale check + autograd's ones_like (~5 us at cfg 2)
+    kernel_ms = extra.get("operator_ms_per_step", ms_per_step)
+    achieved = balg / (kernel_ms * 1e-3) / 1e9
     kernels = {"dense": "k_fused<exact,dense> (+ k_rescale no-op check)" if args.workload in ("c2", "c3d") else
                         "k_gather + k_wavefront + k_expand (8-group stream pipeline) + k_loss_sum + k_rescale check",
                "gather": "k_fused<exact,pairs> + k_expand<1>" if args.workload in ("c2g", "c3") else "general path + k_expand<1>",
-               "compact": "k_prefix + k_gather + k_wavefront + k_grads_pairs + k_expand<2>"}[mode]
+               "compact": "k_prefix + k_gather + k_wavefront + k_grads_pairs + k_expand<2>",
+               "bf16": "k_fused<exact,dense,bf16>" if args.workload == "c2b" else "k_gather<bf16> + k_wavefront + k_expand<0,bf16>",
+               "logits": "k_lse_pairs + k_fused<exact,pairs> + k_expand_logits"}[mode]
     out = {
         "metric": "RNN-T loss+grad lattices/sec", "value": value, "unit": "lattices/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 i/o, f32 accumulate" if mode == "bf16" else "f32", "data": "synthetic",
         "config": config_dict(args.workload, desc, N, T, U, V, world, R, R * per_set / 1e6),
         "timed_call": API_CALL[mode] + " -- " + graph_note,
         "lse_mode": args.lse + (" (= exact: results bit-identical to the reference kernels)" if args.lse == "auto" else ""),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "traffic_note": "not measured in this run; ncu dram__bytes per launch are in profiles/",
-                     "algorithmic_bytes_per_launch": balg, "peak_source": peak_src, "kernel": kernels},
+                     "algorithmic_bytes_per_launch": balg, "peak_source": peak_src, "kernel": kernels,
+                     "kernel_ms": kernel_ms,
+                     "kernel_ms_source": ("CUDA events over back-to-back operator calls (_C.rnnt_loss = the one kernel)"
+                                          if "operator_ms_per_step" in extra else "the timed step (all its kernels)")},
         "e2e": {"value": N * world * ke / e2e_s, "unit": "lattices/s", "h2d_bytes_per_step": hb,
                 "d2h_bytes_per_step": 4, "steps": ke, "ms_per_step": e2e_s / ke * 1e3,
                 "call": "pinned host tensors -> device copies -> " + API_CALL[mode] + " -> loss.item()"},
@@ -427,8 +474,21 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_oracle_rate(N, T, U, V)
     print(json.dumps(out), flush=True)
+    finish(world, dist)
+
+
+def finish(world, dist):
+    """Multi-rank exit: every rank has done its work and rank 0 has printed; leave without tearing NCCL down (destroying
+    the communicator after CUDA graphs were captured on it hung the watchdog for minutes on this stack)."""
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_c5(w, parallel, dist, dev, world, rank, steps=4, warm=2):
@@ -438,16 +498,19 @@ def run_c5(w, parallel, dist, dev, world, rank, steps=4, warm=2):
     one 11.8 GB input buffer serves all micro-batches (far larger than L2)."""
     N, T, U, V, MB = 32, 600, 150, 1024, 8
     g = torch.Generator(device=dev).manual_seed(5 + rank)
-    x = torch.log_softmax(torch.randn((N, T, U, V), device=dev, generator=g), dim=-1).requires_grad_(True)
+    x = torch.log_softmax(torch.randn((N, T, U, V), device=dev, generator=g), dim=-1)
     ys = torch.randint(1, V, (N, U - 1), dtype=torch.int, device=dev, generator=g)
     xn = torch.full((N,), T, dtype=torch.int, device=dev)
     yn = torch.full((N,), U - 1, dtype=torch.int, device=dev)
     total = N * MB * world
 
+    x.requires_grad_(False)
+
     def step(i):
-        x.grad = None
-        return parallel.rnnt_loss_microbatches(((x, ys, xn, yn) for _ in range(MB)), global_batch=total,
-                                               reduction="mean")
+        # every micro-batch is its own leaf over the same 11.8 GB of synthetic log-probs (no copy): its gradient is a
+        # fresh tensor, as it would be for distinct micro-batches
+        return parallel.rnnt_loss_microbatches(((x.detach().requires_grad_(True), ys, xn, yn) for _ in range(MB)),
+                                               global_batch=total, reduction="mean")
     for i in range(warm):
         step(i)
     ms = timed(step, steps, world, dist, dev) / steps

@@ -116,8 +116,19 @@ int rnnt_b200_loss_dense_reduced(void *stream, void *workspace, size_t workspace
  * differ (stride 0: one upstream scalar for all samples).  Replaces RNNTLoss.backward's dense mul_
  * (__init__.py:21-24): when the upstream gradient equals what the forward already multiplied in (the usual
  * loss.backward()), no memory is touched.  With applied == NULL the product is exactly the reference's. */
-int rnnt_b200_rescale(void *stream, float *grads, const float *grad_out, int grad_out_stride,
-                      const float *applied, int N, int64_t elems_per_sample);
+int rnnt_b200_rescale(void *stream, void *grads, const float *grad_out, int grad_out_stride,
+                      const float *applied, int N, int64_t elems_per_sample, int elem_bytes /* 4 = f32, 2 = bf16 */);
+
+/* Half-precision I/O (the reference is fp32-only, binding.cpp:17-19, __init__.py:111):
+ * rnnt_b200_loss_dense_reduced with log_probs (N,T,U,V) and grads (N,T,U,V) in bfloat16.  alpha, beta, costs and all
+ * arithmetic stay fp32 (the gradient is rounded to bf16 once, on the final store), so costs equal the fp32 path's on
+ * the same (bf16-representable) inputs and the gradient is within bf16 rounding (2^-9 relative) of it.  Halves both
+ * the algorithmic and the physical bytes of the path; grads is required (forward-only callers use the fp32 entry). */
+int rnnt_b200_loss_dense_bf16(void *stream, void *workspace, size_t workspace_bytes,
+                              const void *log_probs_bf16, const int *labels, const int *xn, const int *yn,
+                              float *costs, void *grads_bf16, const float *grad_scale, float *loss_sum,
+                              unsigned int *sync_counter, int N, int T, int U, int V, int blank,
+                              float fastemit_lambda, int lse_mode);
 
 /* Gathered layout (N,T,U,2) = [blank, label] per cell.  Replaces run_warp_rnnt_gather
  * (core.h:35-39).  pair_grads (N,T,U,2) out, fully written (zeros on padding); NULL = fwd only. */

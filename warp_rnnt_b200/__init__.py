@@ -237,7 +237,9 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=
     """The RNN-Transducer loss (same signature and semantics as the reference, __init__.py:57-143).
 
     Args:
-        log_probs: (N, T, U, V) float32 log-softmaxed joint output; compact: (STU, V).
+        log_probs: (N, T, U, V) float32 log-softmaxed joint output; compact: (STU, V).  The dense path
+            (gather=False, compact=False) also takes bfloat16: bf16 in, bf16 gradient out, float32 costs and
+            arithmetic (the reference is float32-only, binding.cpp:17-19).
         labels: (N, U-1) int32; compact: (sum(labels_lengths),).
         frames_lengths, labels_lengths: (N,) int32.
         average_frames: divide each sample's loss by its number of frames.
@@ -264,6 +266,7 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=
                                       fastemit_lambda,
                                       (log_probs.requires_grad and torch.is_grad_enabled()))
     elif gather:
+        assert log_probs.dtype == torch.float32, "gather=True takes float32 log_probs (bfloat16: gather=False)"
         costs = RNNTLossGather.apply(log_probs, labels, frames_lengths, labels_lengths, blank, fastemit_lambda)
     else:
         # dense path: the reduction below is folded into the one kernel launch (see RNNTLoss)
@@ -271,12 +274,12 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=
             raise ValueError(
                 f"Unknown reduction method: {reduction}, expected to be one of ['mean', 'sum', 'none']")
         reduce = reduction in ("mean", "sum")
-        weights = None
+        weights = None                                   # float32 also for bfloat16 log_probs (costs are float32)
         if average_frames:
-            weights = 1.0 / frames_lengths.to(log_probs)
+            weights = 1.0 / frames_lengths.to(torch.float32)
         if reduction == "mean":
             n = max(int(log_probs.size(0)), 1)
-            weights = torch.full((log_probs.size(0),), 1.0 / n, dtype=log_probs.dtype, device=log_probs.device) \
+            weights = torch.full((log_probs.size(0),), 1.0 / n, dtype=torch.float32, device=log_probs.device) \
                 if weights is None else weights / n
         return RNNTLoss.apply(log_probs, labels, frames_lengths, labels_lengths, blank, fastemit_lambda, weights,
                               reduce)

@@ -161,6 +161,95 @@ static Pipeline *get_pipeline_locked() {
 
 using namespace rnnt;
 
+// dense layout, log_probs / grads of 4-byte (f32) or 2-byte (bf16) elements
+static int loss_dense_any(void *stream, void *workspace, size_t workspace_bytes, const void *log_probs,
+                          const int *labels, const int *xn, const int *yn, float *costs, void *grads,
+                          const float *grad_scale, float *loss_sum, unsigned int *sync_counter, int N, int T,
+                          int U, int V, int blank, float fastemit_lambda, int lse_mode, int io_bf16) {
+    const size_t esz = io_bf16 ? 2 : 4;
+    auto lp_at = [&](int64_t cell0) { return (const void *)((const char *)log_probs + (size_t)cell0 * V * esz); };
+    auto g_at = [&](int64_t cell0) { return (void *)((char *)grads + (size_t)cell0 * V * esz); };
+    if (io_bf16 && !grads) return RNNT_STATUS_INVALID_ARGUMENT;
+    if (!dense_args_ok(N, T, U, V) || blank < 0 || blank >= V) return RNNT_STATUS_INVALID_ARGUMENT;
+    if (N == 0) return RNNT_STATUS_SUCCESS;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t cells = (int64_t)N * T * U;
+    FusedPlan plan;
+    if (want_fused(N, T, U, &plan)) {
+        RNNT_TRY(launch_fused(s, resolve_kind(lse_mode, false), plan, log_probs, labels, xn, yn, costs, grads, nullptr,
+                              grad_scale, N, T, U, V, blank, fastemit_lambda, 0, 1, nullptr, nullptr, nullptr, loss_sum,
+                              sync_counter, io_bf16),
+                 RNNT_STATUS_WARP_FAILED);
+        if (loss_sum && !sync_counter)                  // no counter: reduce in a second, tiny launch
+            RNNT_TRY(launch_loss_sum(s, costs, grad_scale, N, loss_sum), RNNT_STATUS_COSTS_FAILED);
+        return RNNT_STATUS_SUCCESS;
+    }
+    const Workspace w = carve(workspace, cells, N);
+    if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
+    const int kind = resolve_kind(lse_mode, false);
+    // Large batches of large lattices: software-pipeline lattice groups over internal streams so that the
+    // latency-bound wavefront of group g overlaps the bandwidth-bound gather of g+1 and emit of g-1.
+    const int groups = (grads && N >= 8 && (int64_t)cells * V * 4 >= ((int64_t)512 << 20) && pipeline_enabled())
+                           ? (N >= 32 ? 8 : 4) : 1;
+    if (groups > 1) {
+        std::lock_guard<std::mutex> lock(g_pipe_mu);    // the pipeline's events are shared by all calls on this device
+        Pipeline *pl = get_pipeline_locked();
+        if (pl) {
+            int status = RNNT_STATUS_SUCCESS;
+            cudaEventRecord(pl->fork, s);
+            cudaStreamWaitEvent(pl->gather_s, pl->fork, 0);
+            cudaStreamWaitEvent(pl->expand_s, pl->fork, 0);
+            for (int i = 0; i < Pipeline::kWave; ++i) cudaStreamWaitEvent(pl->wave_s[i], pl->fork, 0);
+            for (int g = 0; g < groups && !status; ++g) {
+                const int n0 = (int)((int64_t)N * g / groups), n1 = (int)((int64_t)N * (g + 1) / groups);
+                const int ng = n1 - n0;
+                const int64_t c0 = (int64_t)n0 * T * U, cg = (int64_t)ng * T * U;
+                Problem p = {xn + n0, yn + n0, nullptr, nullptr, ng, T, U, 0};
+                const int *lab_g = labels + (int64_t)n0 * (U - 1);
+                cudaStream_t ws = pl->wave_s[g % Pipeline::kWave];
+                if (launch_gather(pl->gather_s, p, lp_at(c0), lab_g, V, blank, w.pairs + c0, nullptr, cg, io_bf16) != cudaSuccess)
+                    status = RNNT_STATUS_GATHER_FAILED;
+                cudaEventRecord(pl->gathered[g], pl->gather_s);
+                cudaStreamWaitEvent(ws, pl->gathered[g], 0);
+                if (!status && launch_wavefront(ws, kind, p, w.pairs + c0, w.alphas + c0, w.betas + c0, w.ll + 2 * n0,
+                                                w.bad + n0, costs + n0, 0, 1, T, U) != cudaSuccess)
+                    status = RNNT_STATUS_WARP_FAILED;
+                cudaEventRecord(pl->swept[g], ws);
+                cudaStreamWaitEvent(pl->expand_s, pl->swept[g], 0);
+                ExpandSrc src = {};
+                src.pairs = w.pairs + c0; src.alphas = w.alphas + c0; src.betas = w.betas + c0; src.bad = w.bad + n0;
+                src.scale = grad_scale ? grad_scale + n0 : nullptr; src.labels = lab_g; src.fastemit_lambda = fastemit_lambda;
+                if (!status && launch_expand(pl->expand_s, p, src, g_at(c0), cg, V, blank, true, io_bf16) != cudaSuccess)
+                    status = RNNT_STATUS_GRADS_BLANK_FAILED;
+            }
+            cudaEventRecord(pl->join[0], pl->gather_s);
+            cudaEventRecord(pl->join[1], pl->expand_s);
+            cudaStreamWaitEvent(s, pl->join[0], 0);
+            cudaStreamWaitEvent(s, pl->join[1], 0);
+            for (int i = 0; i < Pipeline::kWave; ++i) {
+                cudaEventRecord(pl->join[2 + i], pl->wave_s[i]);
+                cudaStreamWaitEvent(s, pl->join[2 + i], 0);
+            }
+            if (!status && loss_sum && launch_loss_sum(s, costs, grad_scale, N, loss_sum) != cudaSuccess)
+                status = RNNT_STATUS_COSTS_FAILED;
+            return status;
+        }
+    }
+    Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
+    RNNT_TRY(launch_gather(s, p, log_probs, labels, V, blank, w.pairs, nullptr, cells, io_bf16), RNNT_STATUS_GATHER_FAILED);
+    RNNT_TRY(launch_wavefront(s, kind, p, w.pairs, w.alphas, w.betas, w.ll, w.bad, costs, grads == nullptr, 1, T, U),
+             RNNT_STATUS_WARP_FAILED);
+    if (grads) {
+        ExpandSrc src = {};
+        src.pairs = w.pairs; src.alphas = w.alphas; src.betas = w.betas; src.bad = w.bad;
+        src.scale = grad_scale; src.labels = labels; src.fastemit_lambda = fastemit_lambda;
+        RNNT_TRY(launch_expand(s, p, src, grads, cells, V, blank, false, io_bf16), RNNT_STATUS_GRADS_BLANK_FAILED);
+    }
+    if (loss_sum) RNNT_TRY(launch_loss_sum(s, costs, grad_scale, N, loss_sum), RNNT_STATUS_COSTS_FAILED);
+    return RNNT_STATUS_SUCCESS;
+}
+
+
 extern "C" {
 
 const char *rnnt_b200_version(void) { return "0.1.0 (sm_100a)"; }
@@ -206,90 +295,27 @@ int rnnt_b200_loss_dense_reduced(void *stream, void *workspace, size_t workspace
                                  const int *labels, const int *xn, const int *yn, float *costs, float *grads,
                                  const float *grad_scale, float *loss_sum, unsigned int *sync_counter, int N, int T,
                                  int U, int V, int blank, float fastemit_lambda, int lse_mode) {
-    if (!dense_args_ok(N, T, U, V) || blank < 0 || blank >= V) return RNNT_STATUS_INVALID_ARGUMENT;
-    if (N == 0) return RNNT_STATUS_SUCCESS;
-    cudaStream_t s = (cudaStream_t)stream;
-    const int64_t cells = (int64_t)N * T * U;
-    FusedPlan plan;
-    if (want_fused(N, T, U, &plan)) {
-        RNNT_TRY(launch_fused(s, resolve_kind(lse_mode, false), plan, log_probs, labels, xn, yn, costs, grads, nullptr,
-                              grad_scale, N, T, U, V, blank, fastemit_lambda, 0, 1, nullptr, nullptr, nullptr, loss_sum,
-                              sync_counter),
-                 RNNT_STATUS_WARP_FAILED);
-        if (loss_sum && !sync_counter)                  // no counter: reduce in a second, tiny launch
-            RNNT_TRY(launch_loss_sum(s, costs, grad_scale, N, loss_sum), RNNT_STATUS_COSTS_FAILED);
-        return RNNT_STATUS_SUCCESS;
-    }
-    const Workspace w = carve(workspace, cells, N);
-    if (!workspace || workspace_bytes < w.bytes) return RNNT_STATUS_WORKSPACE_TOO_SMALL;
-    const int kind = resolve_kind(lse_mode, false);
-    // Large batches of large lattices: software-pipeline lattice groups over internal streams so that the
-    // latency-bound wavefront of group g overlaps the bandwidth-bound gather of g+1 and emit of g-1.
-    const int groups = (grads && N >= 8 && (int64_t)cells * V * 4 >= ((int64_t)512 << 20) && pipeline_enabled())
-                           ? (N >= 32 ? 8 : 4) : 1;
-    if (groups > 1) {
-        std::lock_guard<std::mutex> lock(g_pipe_mu);    // the pipeline's events are shared by all calls on this device
-        Pipeline *pl = get_pipeline_locked();
-        if (pl) {
-            int status = RNNT_STATUS_SUCCESS;
-            cudaEventRecord(pl->fork, s);
-            cudaStreamWaitEvent(pl->gather_s, pl->fork, 0);
-            cudaStreamWaitEvent(pl->expand_s, pl->fork, 0);
-            for (int i = 0; i < Pipeline::kWave; ++i) cudaStreamWaitEvent(pl->wave_s[i], pl->fork, 0);
-            for (int g = 0; g < groups && !status; ++g) {
-                const int n0 = (int)((int64_t)N * g / groups), n1 = (int)((int64_t)N * (g + 1) / groups);
-                const int ng = n1 - n0;
-                const int64_t c0 = (int64_t)n0 * T * U, cg = (int64_t)ng * T * U;
-                Problem p = {xn + n0, yn + n0, nullptr, nullptr, ng, T, U, 0};
-                const int *lab_g = labels + (int64_t)n0 * (U - 1);
-                cudaStream_t ws = pl->wave_s[g % Pipeline::kWave];
-                if (launch_gather(pl->gather_s, p, log_probs + c0 * V, lab_g, V, blank, w.pairs + c0, nullptr, cg) != cudaSuccess)
-                    status = RNNT_STATUS_GATHER_FAILED;
-                cudaEventRecord(pl->gathered[g], pl->gather_s);
-                cudaStreamWaitEvent(ws, pl->gathered[g], 0);
-                if (!status && launch_wavefront(ws, kind, p, w.pairs + c0, w.alphas + c0, w.betas + c0, w.ll + 2 * n0,
-                                                w.bad + n0, costs + n0, 0, 1, T, U) != cudaSuccess)
-                    status = RNNT_STATUS_WARP_FAILED;
-                cudaEventRecord(pl->swept[g], ws);
-                cudaStreamWaitEvent(pl->expand_s, pl->swept[g], 0);
-                ExpandSrc src = {};
-                src.pairs = w.pairs + c0; src.alphas = w.alphas + c0; src.betas = w.betas + c0; src.bad = w.bad + n0;
-                src.scale = grad_scale ? grad_scale + n0 : nullptr; src.labels = lab_g; src.fastemit_lambda = fastemit_lambda;
-                if (!status && launch_expand(pl->expand_s, p, src, grads + c0 * V, cg, V, blank, true) != cudaSuccess)
-                    status = RNNT_STATUS_GRADS_BLANK_FAILED;
-            }
-            cudaEventRecord(pl->join[0], pl->gather_s);
-            cudaEventRecord(pl->join[1], pl->expand_s);
-            cudaStreamWaitEvent(s, pl->join[0], 0);
-            cudaStreamWaitEvent(s, pl->join[1], 0);
-            for (int i = 0; i < Pipeline::kWave; ++i) {
-                cudaEventRecord(pl->join[2 + i], pl->wave_s[i]);
-                cudaStreamWaitEvent(s, pl->join[2 + i], 0);
-            }
-            if (!status && loss_sum && launch_loss_sum(s, costs, grad_scale, N, loss_sum) != cudaSuccess)
-                status = RNNT_STATUS_COSTS_FAILED;
-            return status;
-        }
-    }
-    Problem p = {xn, yn, nullptr, nullptr, N, T, U, 0};
-    RNNT_TRY(launch_gather(s, p, log_probs, labels, V, blank, w.pairs, nullptr, cells), RNNT_STATUS_GATHER_FAILED);
-    RNNT_TRY(launch_wavefront(s, kind, p, w.pairs, w.alphas, w.betas, w.ll, w.bad, costs, grads == nullptr, 1, T, U),
-             RNNT_STATUS_WARP_FAILED);
-    if (grads) {
-        ExpandSrc src = {};
-        src.pairs = w.pairs; src.alphas = w.alphas; src.betas = w.betas; src.bad = w.bad;
-        src.scale = grad_scale; src.labels = labels; src.fastemit_lambda = fastemit_lambda;
-        RNNT_TRY(launch_expand(s, p, src, grads, cells, V, blank), RNNT_STATUS_GRADS_BLANK_FAILED);
-    }
-    if (loss_sum) RNNT_TRY(launch_loss_sum(s, costs, grad_scale, N, loss_sum), RNNT_STATUS_COSTS_FAILED);
-    return RNNT_STATUS_SUCCESS;
+    return loss_dense_any(stream, workspace, workspace_bytes, log_probs, labels, xn, yn, costs, grads, grad_scale,
+                          loss_sum, sync_counter, N, T, U, V, blank, fastemit_lambda, lse_mode, 0);
 }
 
-int rnnt_b200_rescale(void *stream, float *grads, const float *grad_out, int grad_out_stride, const float *applied,
-                      int N, int64_t elems_per_sample) {
-    if (N < 0 || elems_per_sample < 0 || grad_out_stride < 0 || grad_out_stride > 1 || !grads || !grad_out)
+int rnnt_b200_loss_dense_bf16(void *stream, void *workspace, size_t workspace_bytes, const void *log_probs_bf16,
+                              const int *labels, const int *xn, const int *yn, float *costs, void *grads_bf16,
+                              const float *grad_scale, float *loss_sum, unsigned int *sync_counter, int N, int T,
+                              int U, int V, int blank, float fastemit_lambda, int lse_mode) {
+    if ((reinterpret_cast<uintptr_t>(log_probs_bf16) | reinterpret_cast<uintptr_t>(grads_bf16)) & 1u)
         return RNNT_STATUS_INVALID_ARGUMENT;
-    RNNT_TRY(launch_rescale((cudaStream_t)stream, grads, grad_out, grad_out_stride, applied, N, elems_per_sample),
+    return loss_dense_any(stream, workspace, workspace_bytes, log_probs_bf16, labels, xn, yn, costs, grads_bf16,
+                          grad_scale, loss_sum, sync_counter, N, T, U, V, blank, fastemit_lambda, lse_mode, 1);
+}
+
+int rnnt_b200_rescale(void *stream, void *grads, const float *grad_out, int grad_out_stride, const float *applied,
+                      int N, int64_t elems_per_sample, int elem_bytes) {
+    if (N < 0 || elems_per_sample < 0 || grad_out_stride < 0 || grad_out_stride > 1 || !grads || !grad_out ||
+        (elem_bytes != 4 && elem_bytes != 2))
+        return RNNT_STATUS_INVALID_ARGUMENT;
+    RNNT_TRY(launch_rescale((cudaStream_t)stream, grads, grad_out, grad_out_stride, applied, N, elems_per_sample,
+                            elem_bytes == 2),
              RNNT_STATUS_GRADS_BLANK_FAILED);
     return RNNT_STATUS_SUCCESS;
 }

@@ -22,13 +22,15 @@
 
 namespace {
 
-void check4(const at::Tensor &xs, const at::Tensor &ys, const at::Tensor &xn, const at::Tensor &yn) {
+void check4(const at::Tensor &xs, const at::Tensor &ys, const at::Tensor &xn, const at::Tensor &yn,
+            bool allow_bf16 = false) {
     // order as in the reference (binding.cpp:31-46): contiguity, then dtypes, then device
     TORCH_CHECK(xs.is_contiguous(), "xs must be contiguous");
     TORCH_CHECK(ys.is_contiguous(), "ys must be contiguous");
     TORCH_CHECK(xn.is_contiguous(), "xn must be contiguous");
     TORCH_CHECK(yn.is_contiguous(), "yn must be contiguous");
-    TORCH_CHECK(xs.scalar_type() == at::ScalarType::Float, "xs must be a Float tensor");
+    TORCH_CHECK(xs.scalar_type() == at::ScalarType::Float || (allow_bf16 && xs.scalar_type() == at::ScalarType::BFloat16),
+                "xs must be a Float tensor");
     TORCH_CHECK(ys.scalar_type() == at::ScalarType::Int, "ys must be a Int tensor");
     TORCH_CHECK(xn.scalar_type() == at::ScalarType::Int, "xn must be a Int tensor");
     TORCH_CHECK(yn.scalar_type() == at::ScalarType::Int, "yn must be a Int tensor");
@@ -78,14 +80,17 @@ unsigned int *next_sync_counter(const at::Tensor &like) {
 std::tuple<at::Tensor, at::Tensor> loss_dense_impl(const at::Tensor &xs, const at::Tensor &ys, const at::Tensor &xn,
                                                    const at::Tensor &yn, int blank, float fastemit_lambda,
                                                    const c10::optional<at::Tensor> &scale, bool want_grads,
-                                                   int lse_mode, at::Tensor loss_sum = at::Tensor()) {
-    check4(xs, ys, xn, yn);
+                                                   int lse_mode, at::Tensor loss_sum = at::Tensor(),
+                                                   bool allow_bf16 = false) {
+    check4(xs, ys, xn, yn, allow_bf16);
     check_dense_shapes(xs, ys, xn, yn);
     const c10::cuda::CUDAGuard guard(xs.device());
     const int64_t N = xs.size(0), T = xs.size(1), U = xs.size(2), V = xs.size(3);
-    at::Tensor costs = at::empty({N}, xs.options());
+    const bool bf16 = xs.scalar_type() == at::ScalarType::BFloat16;
+    at::Tensor costs = at::empty({N}, xs.options().dtype(at::kFloat));
     at::Tensor grads = want_grads ? at::empty_like(xs) : at::empty({0}, xs.options());
     if (N == 0) return std::make_tuple(costs, grads);
+    TORCH_CHECK(!bf16 || (want_grads && blank != -1), "bfloat16 xs: dense (N,T,U,V) layout with gradients only");
     const float *sc = nullptr;
     if (scale.has_value() && scale->defined()) {
         TORCH_CHECK(scale->is_contiguous() && scale->scalar_type() == at::ScalarType::Float &&
@@ -108,6 +113,13 @@ std::tuple<at::Tensor, at::Tensor> loss_dense_impl(const at::Tensor &xs, const a
         TORCH_CHECK(blank >= 0 && blank < V, "blank must be in [0, V) (or -1 for the gathered layout)");
         at::Tensor ws = workspace_for(xs, N * T * U, N);
         float *ls = loss_sum.defined() ? loss_sum.data_ptr<float>() : nullptr;
+        if (bf16)
+            status = rnnt_b200_loss_dense_bf16(current_stream(xs), ws.data_ptr(), (size_t)ws.numel(), xs.data_ptr(),
+                                               ys.data_ptr<int>(), xn.data_ptr<int>(), yn.data_ptr<int>(),
+                                               costs.data_ptr<float>(), grads.data_ptr(), sc, ls,
+                                               ls ? next_sync_counter(xs) : nullptr, (int)N, (int)T, (int)U, (int)V,
+                                               blank, fastemit_lambda, lse_mode);
+        else
         status = rnnt_b200_loss_dense_reduced(current_stream(xs), ws.data_ptr(), (size_t)ws.numel(), xs.data_ptr<float>(),
                                               ys.data_ptr<int>(), xn.data_ptr<int>(), yn.data_ptr<int>(),
                                               costs.data_ptr<float>(), want_grads ? grads.data_ptr<float>() : nullptr,
@@ -219,15 +231,16 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> rnnt_loss_fused(const at::Tensor 
     const c10::cuda::CUDAGuard guard(xs.device());
     at::Tensor loss = at::empty({1}, xs.options().dtype(at::kFloat));
     if (xs.dim() == 4 && xs.size(0) == 0) loss.zero_();
-    auto r = loss_dense_impl(xs, ys, xn, yn, blank, fastemit_lambda, grad_scale, want_grads, lse_mode, loss);
+    auto r = loss_dense_impl(xs, ys, xn, yn, blank, fastemit_lambda, grad_scale, want_grads, lse_mode, loss, true);
     return std::make_tuple(std::get<0>(r), std::get<1>(r), loss);
 }
 
 // in place: grads[n] *= grad_out[n] / applied[n] where they differ (grad_out with one element: one scalar for all)
 void rnnt_rescale_(at::Tensor grads, const at::Tensor &grad_out, const c10::optional<at::Tensor> &applied) {
-    TORCH_CHECK(grads.is_contiguous() && grads.scalar_type() == at::ScalarType::Float && grads.device().is_cuda() &&
-                    grads.dim() >= 1,
-                "grads must be a contiguous CUDA Float tensor");
+    const bool bf16 = grads.scalar_type() == at::ScalarType::BFloat16;
+    TORCH_CHECK(grads.is_contiguous() && (grads.scalar_type() == at::ScalarType::Float || bf16) &&
+                    grads.device().is_cuda() && grads.dim() >= 1,
+                "grads must be a contiguous CUDA Float (or BFloat16) tensor");
     const int64_t N = grads.size(0);
     TORCH_CHECK(grad_out.is_contiguous() && grad_out.scalar_type() == at::ScalarType::Float &&
                     grad_out.device() == grads.device() && (grad_out.numel() == N || grad_out.numel() == 1),
@@ -241,8 +254,9 @@ void rnnt_rescale_(at::Tensor grads, const at::Tensor &grad_out, const c10::opti
     }
     if (N == 0) return;
     const c10::cuda::CUDAGuard guard(grads.device());
-    check_status(rnnt_b200_rescale(current_stream(grads), grads.data_ptr<float>(), grad_out.data_ptr<float>(),
-                                   (grad_out.numel() == 1 && N != 1) ? 0 : 1, ap, (int)N, grads.numel() / N));
+    check_status(rnnt_b200_rescale(current_stream(grads), grads.data_ptr(), grad_out.data_ptr<float>(),
+                                   (grad_out.numel() == 1 && N != 1) ? 0 : 1, ap, (int)N, grads.numel() / N,
+                                   bf16 ? 2 : 4));
 }
 
 std::tuple<at::Tensor, at::Tensor> rnnt_gather_forward(const at::Tensor &xs, const at::Tensor &ys,

@@ -86,10 +86,26 @@ __device__ __forceinline__ void stage_row(const Problem &p, const ExpandSrc &src
 // MODE 0: dense layout, source = alpha/beta/pairs (forward)            label overrides blank
 // MODE 1: dense layout, source = pair grads (gather=True backward)     label adds to blank (scatter_add)
 // MODE 2: compact layout, source = pair grads + loc (compact backward) label written iff loc != blank
-template <int MODE>
+// 16-byte streaming store of VEC output elements (4 floats or 8 bf16)
+__device__ __forceinline__ void st_vec(float *p, const float (&e)[4]) { st_cs_v4(p, make_float4(e[0], e[1], e[2], e[3])); }
+__device__ __forceinline__ void st_vec(__nv_bfloat16 *p, const float (&e)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(e[2 * k], e[2 * k + 1]);
+        w[k] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+__device__ __forceinline__ void st_one(float *p, float v) { st_cs(p, v); }
+__device__ __forceinline__ void st_one(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+
+// OUT: element type of the dense output (float; __nv_bfloat16 for the bf16 i/o forward, MODE 0)
+template <int MODE, typename OUT = float>
 __global__ void __launch_bounds__(kExpandThreads)
-k_expand(Problem p, ExpandSrc src, float *__restrict__ out, int64_t cells, int V, int blank, int rows_per_chunk,
+k_expand(Problem p, ExpandSrc src, OUT *__restrict__ out, int64_t cells, int V, int blank, int rows_per_chunk,
          FastDiv divV, FastDiv divU, FastDiv divTU, int vec_ok) {
+    constexpr int VEC = 16 / (int)sizeof(OUT);          // output elements per 16-byte vector
     __shared__ float2 s_g[kExpandMaxRows];
     __shared__ int s_lab[kExpandMaxRows];
     const int64_t nchunks = (cells + rows_per_chunk - 1) / rows_per_chunk;
@@ -117,25 +133,25 @@ k_expand(Problem p, ExpandSrc src, float *__restrict__ out, int64_t cells, int V
             if (v == lab) x = (MODE == 1 && src.label_adds) ? x + g.y : ((MODE == 1 && g.y == 0.0f) ? x : g.y);
             return x;
         };
-        int64_t a0 = vec_ok ? min(f1, (f0 + 3) & ~(int64_t)3) : f1;
-        int64_t a1 = vec_ok ? max(a0, f1 & ~(int64_t)3) : f1;
-        // head and tail scalars (at most 3 each when vec_ok)
+        int64_t a0 = vec_ok ? min(f1, (f0 + VEC - 1) & ~(int64_t)(VEC - 1)) : f1;
+        int64_t a1 = vec_ok ? max(a0, f1 & ~(int64_t)(VEC - 1)) : f1;
+        // head and tail scalars (fewer than VEC each when vec_ok)
         for (int64_t f = f0 + threadIdx.x; f < a0; f += kExpandThreads) {
             const uint32_t local = (uint32_t)(f - f0);
             const uint32_t row = divV.div(local);
-            st_cs(out + f, value((int)row, (int)(local - row * V)));
+            st_one(out + f, value((int)row, (int)(local - row * V)));
         }
         for (int64_t f = a1 + threadIdx.x; f < f1; f += kExpandThreads) {
             const uint32_t local = (uint32_t)(f - f0);
             const uint32_t row = divV.div(local);
-            st_cs(out + f, value((int)row, (int)(local - row * V)));
+            st_one(out + f, value((int)row, (int)(local - row * V)));
         }
-        for (int64_t f = a0 + 4 * (int64_t)threadIdx.x; f < a1; f += 4 * kExpandThreads) {
+        for (int64_t f = a0 + VEC * (int64_t)threadIdx.x; f < a1; f += VEC * kExpandThreads) {
             const uint32_t local = (uint32_t)(f - f0);
             uint32_t row = divV.div(local);
             int v = (int)(local - row * V);
-            float e[4];
-            if ((V & 3) == 0) {
+            float e[VEC];
+            if ((V & (VEC - 1)) == 0) {
                 // rows are whole vectors: one staged-row fetch, four compare/selects.  (Kernel-uniform
                 // test on purpose: a per-vector "does it straddle a row end" branch makes nearly every
                 // warp run both paths -- measured 15 % slower at V = 50.  Also tried and dropped: composing
@@ -147,19 +163,19 @@ k_expand(Problem p, ExpandSrc src, float *__restrict__ out, int64_t cells, int V
                 const bool adds = (MODE == 1) && src.label_adds;
                 const bool lab_live = (MODE != 1) || adds || (g.y != 0.0f);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < VEC; ++k) {
                     float x = (k == pb) ? g.x : 0.0f;
                     if (k == pl && lab_live) x = adds ? x + g.y : g.y;
                     e[k] = x;
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < VEC; ++k) {
                     e[k] = value((int)row, v);
                     if (++v == V) { v = 0; ++row; }
                 }
             }
-            st_cs_v4(out + f, make_float4(e[0], e[1], e[2], e[3]));
+            st_vec(out + f, e);
         }
     }
 }
@@ -181,6 +197,19 @@ __global__ void __launch_bounds__(32) k_loss_sum(const float *__restrict__ costs
 }
 
 constexpr int kRescaleThreads = 256;
+__global__ void __launch_bounds__(kRescaleThreads)
+k_rescale_bf16(__nv_bfloat16 *__restrict__ grads, const float *__restrict__ grad_out, int go_stride,
+               const float *__restrict__ applied, int64_t elems) {
+    const int n = blockIdx.y;
+    const float target = grad_out[(int64_t)n * go_stride];
+    const float cur = applied ? applied[n] : 1.0f;
+    if (target == cur) return;
+    const float f = (cur == 1.0f) ? target : target / cur;
+    __nv_bfloat16 *g = grads + (int64_t)n * elems;
+    for (int64_t i = (int64_t)blockIdx.x * kRescaleThreads + threadIdx.x; i < elems; i += (int64_t)gridDim.x * kRescaleThreads)
+        g[i] = __float2bfloat16_rn(__bfloat162float(g[i]) * f);
+}
+
 __global__ void __launch_bounds__(kRescaleThreads)
 k_rescale(float *__restrict__ grads, const float *__restrict__ grad_out, int go_stride, const float *__restrict__ applied,
           int64_t elems) {
@@ -208,23 +237,25 @@ cudaError_t launch_loss_sum(cudaStream_t s, const float *costs, const float *sca
     return cudaGetLastError();
 }
 
-cudaError_t launch_rescale(cudaStream_t s, float *grads, const float *grad_out, int grad_out_stride, const float *applied,
-                           int N, int64_t elems_per_sample) {
+cudaError_t launch_rescale(cudaStream_t s, void *grads, const float *grad_out, int grad_out_stride, const float *applied,
+                           int N, int64_t elems_per_sample, int io_bf16) {
     if (N <= 0 || elems_per_sample <= 0) return cudaSuccess;
     const int sms = sm_count(current_device());
     int64_t gx = (elems_per_sample / 4 + kRescaleThreads * 8 - 1) / (kRescaleThreads * 8);
     const int64_t cap = ((int64_t)sms * 8 + N - 1) / N;
     gx = max((int64_t)1, min(gx, cap));
     dim3 grid((unsigned)gx, (unsigned)N);
-    k_rescale<<<grid, kRescaleThreads, 0, s>>>(grads, grad_out, grad_out_stride, applied, elems_per_sample);
+    if (io_bf16) k_rescale_bf16<<<grid, kRescaleThreads, 0, s>>>(static_cast<__nv_bfloat16 *>(grads), grad_out, grad_out_stride, applied, elems_per_sample);
+    else k_rescale<<<grid, kRescaleThreads, 0, s>>>(static_cast<float *>(grads), grad_out, grad_out_stride, applied, elems_per_sample);
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src, float *out, int64_t cells,
-                          int V, int blank, bool retire_early) {
+cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src, void *out_v, int64_t cells,
+                          int V, int blank, bool retire_early, int io_bf16) {
+    float *out = static_cast<float *>(out_v);
     if (cells <= 0) return cudaSuccess;
-    int rows = (int)(65536 / ((int64_t)V * 4));
+    int rows = (int)(65536 / ((int64_t)V * (io_bf16 ? 2 : 4)));
     rows = max(1, min(rows, kExpandMaxRows));
     const int64_t nchunks = (cells + rows - 1) / rows;
     const int sms = sm_count(current_device());
@@ -235,6 +266,13 @@ cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src
     const FastDiv divV((uint32_t)V), divU((uint32_t)max(p.U, 1)), divTU((uint32_t)max(p.T * p.U, 1));
     const int vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) ? 1 : 0;
     const int mode = p.compact ? 2 : (src.pg ? 1 : 0);
+    if (io_bf16) {
+        if (mode != 0) return cudaErrorInvalidValue;    // bf16 output: the dense forward emit only
+        k_expand<0, __nv_bfloat16><<<grid, kExpandThreads, 0, s>>>(p, src, static_cast<__nv_bfloat16 *>(out_v), cells, V, blank, rows, divV,
+                                                               divU, divTU, vec_ok);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (mode == 0) k_expand<0><<<grid, kExpandThreads, 0, s>>>(p, src, out, cells, V, blank, rows, divV, divU, divTU, vec_ok);
     else if (mode == 1) k_expand<1><<<grid, kExpandThreads, 0, s>>>(p, src, out, cells, V, blank, rows, divV, divU, divTU, vec_ok);
     else k_expand<2><<<grid, kExpandThreads, 0, s>>>(p, src, out, cells, V, blank, rows, divV, divU, divTU, vec_ok);

@@ -54,6 +54,13 @@ __device__ __forceinline__ float ldg_hint(const float *ptr, uint64_t pol) {
     asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(ptr), "l"(pol));
     return v;
 }
+template <typename IO> __device__ __forceinline__ float ldg_hint_io(const IO *ptr, uint64_t pol);
+template <> __device__ __forceinline__ float ldg_hint_io<float>(const float *ptr, uint64_t pol) { return ldg_hint(ptr, pol); }
+template <> __device__ __forceinline__ float ldg_hint_io<__nv_bfloat16>(const __nv_bfloat16 *ptr, uint64_t pol) {
+    unsigned short v;
+    asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(ptr), "l"(pol));
+    return __uint_as_float((uint32_t)v << 16);
+}
 __device__ __forceinline__ float2 ldg_hint2(const float2 *ptr, uint64_t pol) {
     float2 v;
     asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(ptr), "l"(pol));
@@ -203,13 +210,13 @@ __device__ __forceinline__ void loss_reduce_last(const float *costs, const float
 }
 
 struct FusedArgs {
-    const float *lp;        // dense (N,T,U,V) or, pairs_in, (N,T,U,2)
+    const void *lp;         // dense (N,T,U,V) of the kernel's IO type (f32 / bf16) or, pairs_in, (N,T,U,2) f32
     const int *labels;      // (N,U-1); compact: (sum yn)
     const int64_t *mem_pref, *lab_pref;   // compact layout: first cell / first label of lattice n (else null)
     int64_t *loc;           // compact layout: label id per cell (core_compact.cu:424-431), or null
     const int *xn, *yn;
     float *costs;           // (N)
-    float *grads;           // MODE 0: dense (N,T,U,V)
+    void *grads;            // MODE 0: dense (N,T,U,V) of the kernel's IO type
     float2 *pair_grads;     // MODE 1: (N,T,U) float2
     const float *scale;     // (N) or null
     int N, T, U, V, blank;
@@ -223,7 +230,6 @@ struct FusedArgs {
     int gw;                 // warps that gather (of the 14 non-wavefront warps); MODE 0: the rest start the zero-fill at once
     int tma_fill;           // MODE 0: zero-fill with bulk shared->global copies (else 256-bit STG)
     int fill_warps;         // MODE 0, bulk fill: how many of the 14 free warps issue it (the others chase at once)
-    int debug;              // bit 0: skip the patch stores (timing experiments only; results are wrong)
     long long *trace;       // optional per-CTA phase stamps (clock64), 8 per CTA; null = off
     float *loss_sum;        // optional: sum_n costs[n] * (scale ? scale[n] : 1), written by the last CTA to finish
     unsigned *sync_counter; // with loss_sum: device counter, 0 on entry, left 0 (self-resetting)
@@ -376,8 +382,11 @@ __device__ __forceinline__ void sweep_diag(uint32_t wb, uint32_t wl, uint32_t ou
 }
 
 // MODE 0: dense gradients (zero-fill + patch).  MODE 1: (N,T,U,2) gradients.  Both write costs.
-template <int KIND, int MODE, int C>
+// IO: element type of log_probs and of the dense gradient (float, or __nv_bfloat16 with MODE 0).
+template <int KIND, int MODE, int C, typename IO = float>
 __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
+    constexpr int ESZ = (int)sizeof(IO);
+    const IO *const lp_io = static_cast<const IO *>(A.lp);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.y, slice = blockIdx.x;
@@ -423,7 +432,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
     const int64_t lab0 = compact ? A.lab_pref[n] : (int64_t)n * (U - 1);
     // TMA rows need 16-byte aligned, 16-byte multiple rows: always true when chosen for the dense layout,
     // per lattice in the compact layout
-    const bool use_tma = A.nbuf > 0 && (!compact || ((((slab * V) | ((int64_t)Un * V)) & 3) == 0));
+    const bool use_tma = A.nbuf > 0 && (!compact || ((((slab * V) | ((int64_t)Un * V)) & (16 / ESZ - 1)) == 0));
 
     // ---- phase 0: sentinels, labels, gather
     if (tid == 0) { s_next = 0; s_bad = ok ? 0 : 1; s_prog[0] = 0; s_prog[1] = 0; }
@@ -467,14 +476,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         if (ok && lw >= 2 && lw < 2 + A.gwn) {
             const int g = lw - 2, NB = A.nb_per;
             const uint64_t pol_first = policy_evict_first();
-            const uint32_t bytes = ((uint32_t)(Un * V) * 4u + 15u) & ~15u;   // <= U*V*4, which is a multiple of 16
-            auto buf_of = [&](int slot) { return reinterpret_cast<const float *>(smem_raw + A.row_off + (size_t)(g * NB + slot) * A.row_stride); };
+            const uint32_t bytes = ((uint32_t)(Un * V) * (uint32_t)ESZ + 15u) & ~15u;   // <= U*V*ESZ, which is a multiple of 16
+            auto buf_of = [&](int slot) { return reinterpret_cast<const IO *>(smem_raw + A.row_off + (size_t)(g * NB + slot) * A.row_stride); };
             auto row_of = [&](int k) { return (k & 1) ? T1 - (k >> 1) : (k >> 1); };   // rows alternate: top, bottom, top, ...
             auto issue = [&](int k, int slot) {
                 if (lane == 0) {
                     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[g * NB + slot]);
                     mbar_expect_tx(bar, bytes);
-                    bulk_load((uint32_t)__cvta_generic_to_shared(buf_of(slot)), A.lp + (slab + (int64_t)row_of(k) * RS) * V, bytes, bar, pol_first);
+                    bulk_load((uint32_t)__cvta_generic_to_shared(buf_of(slot)), lp_io + (slab + (int64_t)row_of(k) * RS) * V, bytes, bar, pol_first);
                 }
             };
             for (int j = 0; j < NB; ++j)
@@ -483,15 +492,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
             int done = 0, slot = 0;
             for (int k = g; k < Tn; k += A.gwn) {
                 const int t = row_of(k);
-                const float *buf = buf_of(slot);
+                const IO *buf = buf_of(slot);
                 const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[g * NB + slot]);
                 // lane 0 waits for the copy, the warp converges behind it (one poller per barrier)
                 if (lane == 0) while (!mbar_try_wait(bar, (phases >> slot) & 1u)) {}
                 __syncwarp();
                 phases ^= 1u << slot;
                 for (int u = lane; u < Un; u += 32) {
-                    const float vb = buf[u * V + A.blank];
-                    const float vl = (u < U1) ? buf[u * V + s_lab[u]] : kBigF;
+                    const float vb = io_to_float<IO>(buf[u * V + A.blank]);
+                    const float vl = (u < U1) ? io_to_float<IO>(buf[u * V + s_lab[u]]) : kBigF;
                     const int ib = idxB(t, u);
                     WBb[ib] = vb;
                     WLb[ib] = vl;                       // kBig on the last column: beta's first column has no column edge
@@ -530,13 +539,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
                 const int64_t cell = slab + (int64_t)t * RS + u;
                 vl[g] = kBigF;
                 if (A.pairs_in) {
-                    const float2 w2 = ldg_hint2(reinterpret_cast<const float2 *>(A.lp) + cell, pol_first);
+                    const float2 w2 = ldg_hint2(static_cast<const float2 *>(A.lp) + cell, pol_first);
                     vb[g] = w2.x;
                     if (u < U1) vl[g] = w2.y;
                 } else {
-                    const float *row = A.lp + cell * V;
-                    vb[g] = ldg_hint(row + A.blank, pol_first);
-                    if (u < U1) vl[g] = ldg_hint(row + s_lab[u], pol_first);
+                    const IO *row = lp_io + cell * V;
+                    vb[g] = ldg_hint_io<IO>(row + A.blank, pol_first);
+                    if (u < U1) vl[g] = ldg_hint_io<IO>(row + s_lab[u], pol_first);
                 }
             }
 #pragma unroll
@@ -571,7 +580,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
                 for (int k = 0; k < 8; ++k) {
                     const int i = min(i0 + 32 * k, T1);
                     const int64_t cell = slab + (beta ? ((int64_t)(T1 - i) * RS + U1) : ((int64_t)max(i - 1, 0) * RS));
-                    v[k] = A.pairs_in ? __ldg(reinterpret_cast<const float2 *>(A.lp) + cell).x : __ldg(A.lp + cell * V + A.blank);
+                    v[k] = A.pairs_in ? __ldg(static_cast<const float2 *>(A.lp) + cell).x : io_load<IO>(lp_io + cell * V + A.blank);
                     if (!beta && i == 0) v[k] = 0.0f;
                 }
 #pragma unroll
@@ -607,14 +616,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
         stamp(beta ? 5 : 4);
     }
     if (MODE == 0) {
-        // zero-fill rows [t0,t1) of this lattice's slab: floats [f0,f1); 32 KB chunks handed out by
-        // s_next; 256-bit evict_last stores on the 32-byte aligned interior
+        // zero-fill rows [t0,t1) of this lattice's slab: elements [f0,f1); 32 KB chunks handed out by
+        // s_next; 256-bit evict_last stores (or bulk copies) on the 32-byte aligned interior
         const int64_t f0 = (slab + (int64_t)t0 * U) * V, f1 = (slab + (int64_t)t1 * U) * V;
-        float *g = A.grads;
+        IO *g = static_cast<IO *>(A.grads);
+        constexpr int EPV = 32 / ESZ;                   // elements per 32 bytes
         const bool vec = ((reinterpret_cast<uintptr_t>(g) & 31u) == 0);
-        const int64_t a0 = vec ? min(f1, (f0 + 7) & ~(int64_t)7) : f1;
-        const int64_t a1 = vec ? max(a0, f1 & ~(int64_t)7) : f1;
-        constexpr int kChunk = 8192;                    // floats per chunk
+        const int64_t a0 = vec ? min(f1, (f0 + EPV - 1) & ~(int64_t)(EPV - 1)) : f1;
+        const int64_t a1 = vec ? max(a0, f1 & ~(int64_t)(EPV - 1)) : f1;
+        constexpr int kChunk = 32768 / ESZ;             // elements per chunk
         const int64_t nfill = (a1 - a0 + kChunk - 1) / kChunk;
         if (A.tma_fill) {
             // the bulk-copy issue blocks when the SM's copy queue is full (the zeros drain at HBM speed), so only
@@ -622,14 +632,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
             if (lane == 0 && (lw < 2 || lw >= 2 + (kFusedThreads / 32 - 2) - A.fill_warps)) {
                 const uint64_t pol = policy_evict_last();
                 const uint32_t zs = (uint32_t)__cvta_generic_to_shared(zbuf);
-                constexpr int piece = kZeroBytes / 4;   // floats per bulk copy
+                constexpr int piece = kZeroBytes / ESZ; // elements per bulk copy
                 for (;;) {
                     const int c = atomicAdd(&s_next, 1);
                     if (c >= nfill) break;
                     const int64_t b = a0 + (int64_t)c * kChunk;
                     const int64_t e = min(a1, b + kChunk);
                     for (int64_t f = b; f < e; f += piece)
-                        bulk_store(g + f, zs, (uint32_t)(min(e - f, (int64_t)piece) * 4), pol);
+                        bulk_store(g + f, zs, (uint32_t)(min(e - f, (int64_t)piece) * ESZ), pol);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -643,12 +653,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
                 const int64_t b = a0 + (int64_t)c * kChunk;
                 const int64_t e = min(a1, b + kChunk);
 #pragma unroll 4
-                for (int64_t f = b + 8 * lane; f < e; f += 256) stg_zero256_evict_last(g + f);
+                for (int64_t f = b + EPV * lane; f < e; f += 32 * EPV) stg_zero256_evict_last(reinterpret_cast<float *>(g + f));
             }
         }
-        if (lw == kFusedThreads / 32 - 1) {             // unaligned head / tail (<= 7 floats each, or all if !vec)
-            for (int64_t f = f0 + lane; f < a0; f += 32) g[f] = 0.0f;
-            for (int64_t f = a1 + lane; f < f1; f += 32) g[f] = 0.0f;
+        if (lw == kFusedThreads / 32 - 1) {             // unaligned head / tail (< 32 bytes each, or everything if !vec)
+            for (int64_t f = f0 + lane; f < a0; f += 32) g[f] = io_from_float<IO>(0.0f);
+            for (int64_t f = a1 + lane; f < f1; f += 32) g[f] = io_from_float<IO>(0.0f);
         }
         stamp(6);
         // ---- chase: while the zeros drain and the two wavefronts run their last diagonals, the 14 free warps follow
@@ -765,7 +775,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
             const int dib = -dq * Wd - (dr >> 1) * (Wd + 1), wib = -Wd + Un * (Wd + 1);
             int64_t off = (slab + (int64_t)(r0 + tt) * RS + (r >> 1)) * V;
             const int64_t doff = ((int64_t)dq * RS + (dr >> 1)) * V, woff = (int64_t)(RS - Un) * V;
-            float *const g = A.grads;
+            IO *const g = static_cast<IO *>(A.grads);
             const double lam1 = 1.0 + (double)A.lam;
             auto patch = [&](auto with_lam) {
                 while (tt < rows) {
@@ -782,8 +792,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_fused(FusedArgs A) {
                         if (decltype(with_lam)::value && which) a = (float)(lam1 * (double)a);
                         float v = -a;
                         if (A.scale) v *= sc;
-                        if (!(A.debug & 1)) g[off + (which ? lab : A.blank)] = v;
-                        else if (v == 123.25f) A.costs[n] = v;
+                        g[off + (which ? lab : A.blank)] = io_from_float<IO>(v);
                     }
                     r += dr; tt += dq; ib += dib; off += doff;
                     if (r >= per) { r -= per; ++tt; ib += wib; off += woff; }
@@ -841,11 +850,11 @@ bool fused_plan(int N, int T, int U, FusedPlan *plan) {
     return true;
 }
 
-template <int KIND, int MODE, int C>
+template <int KIND, int MODE, int C, typename IO = float>
 static cudaError_t launch_fused_kmc(cudaStream_t s, FusedArgs a, size_t smem) {
     static std::atomic<bool> attr_done[kMaxDevices];
     {
-        const cudaError_t e = ensure_dyn_smem(k_fused<KIND, MODE, C>, attr_done, kFusedMaxDynSmem);
+        const cudaError_t e = ensure_dyn_smem(k_fused<KIND, MODE, C, IO>, attr_done, kFusedMaxDynSmem);
         if (e != cudaSuccess) return e;
     }
     if (a.slices > 1) {
@@ -862,7 +871,7 @@ static cudaError_t launch_fused_kmc(cudaStream_t s, FusedArgs a, size_t smem) {
             Occ &o = dev < kMaxDevices ? cache[dev] : local;
             if (o.smem != smem) {
                 int n = 1;
-                o.occ = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fused<KIND, MODE, C>, kFusedThreads, smem) == cudaSuccess && n >= 1) ? n : 1;
+                o.occ = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fused<KIND, MODE, C, IO>, kFusedThreads, smem) == cudaSuccess && n >= 1) ? n : 1;
                 o.smem = smem;
             }
             occ = o.occ;
@@ -870,27 +879,28 @@ static cudaError_t launch_fused_kmc(cudaStream_t s, FusedArgs a, size_t smem) {
         a.slices = max(1, min(a.slices, (occ * sm_count(dev)) / a.N));
     }
     dim3 grid(a.slices, a.N);
-    k_fused<KIND, MODE, C><<<grid, kFusedThreads, smem, s>>>(a);
+    k_fused<KIND, MODE, C, IO><<<grid, kFusedThreads, smem, s>>>(a);
     count_launch();
     return cudaGetLastError();
 }
 
-template <int KIND, int MODE>
+template <int KIND, int MODE, typename IO = float>
 static cudaError_t launch_fused_km(cudaStream_t s, const FusedArgs &a, size_t smem, int C) {   // (a is copied per launch)
     switch (C) {
-        case 1: return launch_fused_kmc<KIND, MODE, 1>(s, a, smem);
-        case 2: return launch_fused_kmc<KIND, MODE, 2>(s, a, smem);
-        case 4: return launch_fused_kmc<KIND, MODE, 4>(s, a, smem);
-        default: return launch_fused_kmc<KIND, MODE, 8>(s, a, smem);
+        case 1: return launch_fused_kmc<KIND, MODE, 1, IO>(s, a, smem);
+        case 2: return launch_fused_kmc<KIND, MODE, 2, IO>(s, a, smem);
+        case 4: return launch_fused_kmc<KIND, MODE, 4, IO>(s, a, smem);
+        default: return launch_fused_kmc<KIND, MODE, 8, IO>(s, a, smem);
     }
 }
 
-cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const float *lp, const int *labels,
-                         const int *xn, const int *yn, float *costs, float *grads, float2 *pair_grads,
+cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const void *lp, const int *labels,
+                         const int *xn, const int *yn, float *costs, void *grads, float2 *pair_grads,
                          const float *scale, int N, int T, int U, int V, int blank, float lam, int pairs_in,
                          int guard, const int64_t *mem_pref, const int64_t *lab_pref, int64_t *loc, float *loss_sum,
-                         unsigned *sync_counter) {
+                         unsigned *sync_counter, int io_bf16) {
     FusedArgs a;
+    if (io_bf16 && (!grads || pairs_in || mem_pref)) return cudaErrorInvalidValue;   // bf16 i/o: dense gradients only
     a.loss_sum = sync_counter ? loss_sum : nullptr; a.sync_counter = sync_counter;
     a.mem_pref = mem_pref; a.lab_pref = lab_pref; a.loc = loc;
     a.lp = lp; a.labels = labels; a.xn = xn; a.yn = yn; a.costs = costs; a.grads = grads; a.pair_grads = pair_grads;
@@ -913,7 +923,7 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
     {
         static const bool want_tma = !env_is("RNNT_B200_GATHER", 'l');
         static const int nb_env = env_int("RNNT_B200_ROW_BUFS", 0);     // tuning knob: row buffers per gather warp (1 or 2)
-        const size_t row = (size_t)U * V * sizeof(float);
+        const size_t row = (size_t)U * V * (io_bf16 ? 2 : sizeof(float));
         const size_t stride = (row + 127) / 128 * 128;
         // keep two CTAs per SM where the plan counted on them
         const size_t cap = (plan.smem <= 110 * 1024) ? (size_t)113 * 1024 : (size_t)kFusedMaxDynSmem;
@@ -936,13 +946,14 @@ cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const 
         a.tma_fill = tma ? 1 : 0;
         static const int fw = env_int("RNNT_B200_FILL_WARPS", 2);
         a.fill_warps = max(1, min(fw, kFusedThreads / 32 - 2));
-        static const int dbg = env_int("RNNT_B200_DEBUG", 0);
-        a.debug = dbg;
     }
     a.trace = g_fused_trace;
     { const GuardPoison gp = guard_poison(); a.poison_n = gp.n; a.poison_delta = gp.delta; }
     const bool dense = grads != nullptr;
     const int C = plan.nw;
+    if (io_bf16)
+        return kind == kFast ? launch_fused_km<kFast, 0, __nv_bfloat16>(s, a, smem, C)
+                             : launch_fused_km<kExactDense, 0, __nv_bfloat16>(s, a, smem, C);
     if (kind == kFast)
         return dense ? launch_fused_km<kFast, 0>(s, a, smem, C) : launch_fused_km<kFast, 1>(s, a, smem, C);
     if (kind == kExactCompact)                          // compact layout: (cells,2) gradients only

@@ -12,8 +12,8 @@ GuardPoison guard_poison();
 
 cudaError_t launch_prefix(cudaStream_t s, const int *xn, const int *yn, int N, int64_t *mem_pref,
                           int64_t *lab_pref, int *totals);
-cudaError_t launch_gather(cudaStream_t s, const Problem &p, const float *lp, const int *labels, int V, int blank,
-                          float2 *pairs, int64_t *loc, int64_t cells_hint);
+cudaError_t launch_gather(cudaStream_t s, const Problem &p, const void *lp, const int *labels, int V, int blank,
+                          float2 *pairs, int64_t *loc, int64_t cells_hint, int io_bf16 = 0);
 cudaError_t launch_wavefront(cudaStream_t s, int kind, const Problem &p, const float2 *pairs, float *alphas,
                              float *betas, float *ws_ll, int *bad, float *costs, int beta_only, int guard,
                              int t_hint, int u_hint);
@@ -37,8 +37,8 @@ struct ExpandSrc {
     float fastemit_lambda;
     int label_adds;          // 1: label == blank accumulates (torch scatter_add semantics of gather=True)
 };
-cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src, float *out, int64_t cells,
-                          int V, int blank, bool retire_early = false);
+cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src, void *out, int64_t cells,
+                          int V, int blank, bool retire_early = false, int io_bf16 = 0);   // io_bf16: bf16 output (forward emit)
 
 // logits.cu -- loss from un-normalised logits (fused log_softmax forward / backward)
 cudaError_t launch_lse_pairs(cudaStream_t s, const float *x, const int *labels, int N, int T, int U, int V, int blank,
@@ -50,16 +50,17 @@ cudaError_t launch_expand_logits(cudaStream_t s, const float *x, const float *ls
 struct FusedPlan { int W, ring, nw, slices; size_t smem; };
 bool fused_plan(int N, int T, int U, FusedPlan *plan);
 void set_fused_trace(long long *buf);   // diagnostics: per-CTA phase stamps of k_fused (8 x clock64 per CTA)
-cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const float *lp, const int *labels,
-                         const int *xn, const int *yn, float *costs, float *grads, float2 *pair_grads,
+cudaError_t launch_fused(cudaStream_t s, int kind, const FusedPlan &plan, const void *lp, const int *labels,
+                         const int *xn, const int *yn, float *costs, void *grads, float2 *pair_grads,
                          const float *scale, int N, int T, int U, int V, int blank, float lam, int pairs_in,
                          int guard, const int64_t *mem_pref = nullptr, const int64_t *lab_pref = nullptr,
                          int64_t *loc = nullptr,   // mem_pref != null: compact layout, T/U = max lengths
-                         float *loss_sum = nullptr, unsigned *sync_counter = nullptr);   // fused sum_n costs[n]*scale[n]
+                         float *loss_sum = nullptr, unsigned *sync_counter = nullptr,    // fused sum_n costs[n]*scale[n]
+                         int io_bf16 = 0);   // log_probs and the dense gradient are bf16 (dense MODE only)
 
 // expand.cu -- small helpers of the python-level API
 cudaError_t launch_loss_sum(cudaStream_t s, const float *costs, const float *scale, int N, float *loss_sum);
-cudaError_t launch_rescale(cudaStream_t s, float *grads, const float *grad_out, int grad_out_stride,
-                           const float *applied, int N, int64_t elems_per_sample);
+cudaError_t launch_rescale(cudaStream_t s, void *grads, const float *grad_out, int grad_out_stride,
+                           const float *applied, int N, int64_t elems_per_sample, int io_bf16 = 0);
 
 }  // namespace rnnt

@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(1024) k_prefix(const int *__restrict__ xn, con
 constexpr int kGatherThreads = 256;
 constexpr int kGatherIlp = 4;
 
+template <typename IO>
 __global__ void __launch_bounds__(kGatherThreads)
-k_gather(Problem p, const float *__restrict__ lp, const int *__restrict__ labels, int V, int blank,
+k_gather(Problem p, const IO *__restrict__ lp, const int *__restrict__ labels, int V, int blank,
          float2 *__restrict__ pairs, int64_t *__restrict__ loc) {
     const int n = blockIdx.y;
     const Lattice L = get_lattice(p, n);
@@ -128,9 +129,9 @@ k_gather(Problem p, const float *__restrict__ lp, const int *__restrict__ labels
 #pragma unroll
         for (int k = 0; k < kGatherIlp; ++k) {
             if (ok[k]) {
-                const float *row = lp + cell[k] * (int64_t)V;
-                vb[k] = __ldg(row + blank);
-                vl[k] = __ldg(row + lab[k]);
+                const IO *row = lp + cell[k] * (int64_t)V;
+                vb[k] = io_load<IO>(row + blank);
+                vl[k] = io_load<IO>(row + lab[k]);
             }
         }
 #pragma unroll
@@ -509,14 +510,15 @@ cudaError_t launch_prefix(cudaStream_t s, const int *xn, const int *yn, int N, i
     return cudaGetLastError();
 }
 
-cudaError_t launch_gather(cudaStream_t s, const Problem &p, const float *lp, const int *labels, int V, int blank,
-                          float2 *pairs, int64_t *loc, int64_t cells_hint) {
+cudaError_t launch_gather(cudaStream_t s, const Problem &p, const void *lp, const int *labels, int V, int blank,
+                          float2 *pairs, int64_t *loc, int64_t cells_hint, int io_bf16) {
     // cells per lattice: dense T*U; compact unknown on the host -> average * 2, grid-stride covers the rest
     int64_t per = p.compact ? (cells_hint / (p.N > 0 ? p.N : 1)) * 2 + 1 : (int64_t)p.T * p.U;
     int gx = (int)((per + kGatherThreads * kGatherIlp - 1) / (kGatherThreads * kGatherIlp));
     gx = max(1, min(gx, 4096));
     dim3 grid(gx, p.N);
-    k_gather<<<grid, kGatherThreads, 0, s>>>(p, lp, labels, V, blank, pairs, loc);
+    if (io_bf16) k_gather<__nv_bfloat16><<<grid, kGatherThreads, 0, s>>>(p, static_cast<const __nv_bfloat16 *>(lp), labels, V, blank, pairs, loc);
+    else k_gather<float><<<grid, kGatherThreads, 0, s>>>(p, static_cast<const float *>(lp), labels, V, blank, pairs, loc);
     count_launch();
     return cudaGetLastError();
 }

@@ -59,6 +59,36 @@ def all_reduce_loss(local_sum, local_count, reduction="mean", group=None):
     return total[0] / total[1].detach()
 
 
+def _local_weighted_sum(log_probs, labels, frames_lengths, labels_lengths, scale, average_frames, blank, gather,
+                        fastemit_lambda, compact, loss_fn):
+    """scale * sum_n cost_n [/ frames_n] of this rank's lattices.  On the default dense path the weights go INTO the
+    kernel launch (the gradient it writes is final and backward touches nothing); otherwise the scale reaches the
+    gradient through the upstream gradient of backward (one more dense pass)."""
+    if loss_fn is None and not gather and not compact:
+        from . import RNNTLoss
+        n = int(frames_lengths.shape[0])
+        weights = torch.full((n,), float(scale), dtype=torch.float32, device=log_probs.device)
+        if average_frames:
+            weights = weights / frames_lengths.to(torch.float32)
+        return RNNTLoss.apply(log_probs, labels, frames_lengths, labels_lengths, blank, fastemit_lambda, weights, True)
+    if loss_fn is None:
+        from . import rnnt_loss as loss_fn
+    local = loss_fn(log_probs, labels, frames_lengths, labels_lengths, average_frames=average_frames,
+                    reduction="sum", blank=blank, gather=gather, fastemit_lambda=fastemit_lambda, compact=compact)
+    return local * scale if scale != 1.0 else local
+
+
+def all_reduce_loss_async(local_sum, group=None):
+    """Start the one collective of the sharded path without blocking the compute stream: in-place SUM all-reduce of the
+    0-d / 1-element ``local_sum`` on NCCL's own stream.  Returns the work handle (``.wait()`` before reading the value)
+    or None when there is nothing to reduce.  The gradients never depend on the reduced VALUE (only on the weights,
+    which are known up front), so a training loop calls ``backward()`` on the LOCAL loss and lets this overlap with the
+    next step's kernel -- a blocking all-reduce sits on the critical path for ~20-30 us per step."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(local_sum, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+
 def rnnt_loss_sharded(log_probs, labels, frames_lengths, labels_lengths, average_frames=False,
                       reduction="mean", blank=0, gather=False, fastemit_lambda=0.0, compact=False,
                       group=None, loss_fn=None, global_batch=None):
@@ -73,14 +103,13 @@ def rnnt_loss_sharded(log_probs, labels, frames_lengths, labels_lengths, average
     the number of lattices over all ranks known to the caller) or 2 elements ('mean' otherwise: sum and count)."""
     if reduction not in ("sum", "mean"):
         raise ValueError("sharded loss supports reduction 'sum' or 'mean', got %r" % (reduction,))
-    if loss_fn is None:
-        from . import rnnt_loss as loss_fn
-    local = loss_fn(log_probs, labels, frames_lengths, labels_lengths, average_frames=average_frames,
-                    reduction="sum", blank=blank, gather=gather, fastemit_lambda=fastemit_lambda,
-                    compact=compact)
     n_local = int(frames_lengths.shape[0])
     if reduction == "mean" and global_batch is not None:
-        return all_reduce_loss(local, n_local, "sum", group) / float(global_batch)
+        local = _local_weighted_sum(log_probs, labels, frames_lengths, labels_lengths, 1.0 / float(global_batch),
+                                    average_frames, blank, gather, fastemit_lambda, compact, loss_fn)
+        return all_reduce_loss(local, n_local, "sum", group)
+    local = _local_weighted_sum(log_probs, labels, frames_lengths, labels_lengths, 1.0, average_frames, blank, gather,
+                                fastemit_lambda, compact, loss_fn)
     return all_reduce_loss(local, n_local, reduction, group)
 
 
@@ -97,19 +126,16 @@ def rnnt_loss_microbatches(batches, global_batch, reduction="mean", average_fram
     ``log_probs.grad`` of every micro-batch that required grad)."""
     if reduction not in ("sum", "mean"):
         raise ValueError("reduction must be 'sum' or 'mean', got %r" % (reduction,))
-    if loss_fn is None:
-        from . import rnnt_loss as loss_fn
     scale = 1.0 / float(global_batch) if reduction == "mean" else 1.0
     total = None
     for log_probs, labels, frames_lengths, labels_lengths in batches:
-        loss = loss_fn(log_probs, labels, frames_lengths, labels_lengths, average_frames=average_frames,
-                       reduction="sum", blank=blank, gather=gather, fastemit_lambda=fastemit_lambda, compact=compact)
+        loss = _local_weighted_sum(log_probs, labels, frames_lengths, labels_lengths, scale, average_frames, blank,
+                                   gather, fastemit_lambda, compact, loss_fn)
         if loss.requires_grad:
-            (loss * scale).backward() if scale != 1.0 else loss.backward()
+            loss.backward()
         total = loss.detach() if total is None else total + loss.detach()
     if total is None:
         raise ValueError("no micro-batches")
-    total = total * scale
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         total = total.reshape(1).clone()
         dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
