@@ -21,8 +21,10 @@ namespace rnnt {
 
 constexpr int kLogitThreads = 256;
 
-// SUB lanes cooperate on one cell (SUB in {1, 8, 32}); online max / sum so the row is read once.
-template <int SUB>
+// SUB lanes cooperate on one cell (SUB in {1, 8, 32}); online max / sum so the row is read once.  VEC4: rows are whole
+// float4s at 16-byte aligned addresses -> the SUB lanes stride over float4s (V = 28: 7 of 8 lanes load one vector each,
+// a warp reads 4 consecutive rows = 448 contiguous bytes).
+template <int SUB, bool VEC4>
 __global__ void __launch_bounds__(kLogitThreads)
 k_lse_pairs(const float *__restrict__ x, const int *__restrict__ labels, int64_t cells, int V, int blank, int U,
             FastDiv divU, FastDiv divTU, float2 *__restrict__ pairs, float *__restrict__ lse_out) {
@@ -32,17 +34,27 @@ k_lse_pairs(const float *__restrict__ x, const int *__restrict__ labels, int64_t
         const int64_t cell = min(base + threadIdx.x / SUB, cells - 1);          // surplus groups redo the last cell (shuffles need every lane)
         const float *row = x + cell * V;
         float m = -INFINITY, s = 0.0f;
-        if (SUB == 1) {
-            // short rows: one thread per cell; neighbouring threads' rows share cache lines, so the pass over v is
-            // served from L1 after the first touch
+        auto add = [&](float a) {
+            if (a > m) { s = s * expf(m - a); m = a; }        // (m == -inf: s is 0, exp(-inf) = 0)
+            s += expf(a - m);
+        };
+        if (VEC4) {
+            const float4 *row4 = reinterpret_cast<const float4 *>(row);
+            for (int q = sub; q < (V >> 2); q += SUB) {
+                const float4 a = __ldg(row4 + q);
+                const float mx = fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w));
+                if (mx > m) { s = s * expf(m - mx); m = mx; }
+                s += (expf(a.x - m) + expf(a.y - m)) + (expf(a.z - m) + expf(a.w - m));
+            }
+        } else if (SUB == 1) {
+            // short unaligned rows: one thread per cell; neighbouring threads' rows share cache lines, so the pass over
+            // v is served from L1 after the first touch
             for (int v = 0; v < V; ++v) m = fmaxf(m, __ldg(row + v));
             for (int v = 0; v < V; ++v) s += expf(__ldg(row + v) - m);
         } else {
-            for (int v = sub; v < V; v += SUB) {
-                const float a = __ldg(row + v);
-                if (a > m) { s = s * expf(m - a); m = a; }    // (m == -inf: s is 0, exp(-inf) = 0)
-                s += expf(a - m);
-            }
+            for (int v = sub; v < V; v += SUB) add(__ldg(row + v));
+        }
+        if (SUB > 1) {
 #pragma unroll
             for (int o = SUB / 2; o > 0; o >>= 1) {
                 const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
@@ -122,12 +134,16 @@ cudaError_t launch_lse_pairs(cudaStream_t s, const float *x, const int *labels, 
     if (cells <= 0) return cudaSuccess;
     const FastDiv divU((uint32_t)U), divTU((uint32_t)(T * U));
     const int sms = sm_count(current_device());
-    const int sub = V <= 48 ? 1 : (V <= 512 ? 8 : 32);
+    const bool vec4 = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+    const int sub = vec4 ? (V <= 32 ? 8 : 32) : (V <= 12 ? 1 : (V <= 512 ? 8 : 32));
     const int64_t per_block = kLogitThreads / sub;
     const int grid = (int)min((cells + per_block - 1) / per_block, (int64_t)sms * 16);
-    if (sub == 1) k_lse_pairs<1><<<grid, kLogitThreads, 0, s>>>(x, labels, cells, V, blank, U, divU, divTU, pairs, lse);
-    else if (sub == 8) k_lse_pairs<8><<<grid, kLogitThreads, 0, s>>>(x, labels, cells, V, blank, U, divU, divTU, pairs, lse);
-    else k_lse_pairs<32><<<grid, kLogitThreads, 0, s>>>(x, labels, cells, V, blank, U, divU, divTU, pairs, lse);
+#define RNNT_LSE_LAUNCH(SUB, VEC) k_lse_pairs<SUB, VEC><<<grid, kLogitThreads, 0, s>>>(x, labels, cells, V, blank, U, divU, divTU, pairs, lse)
+    if (vec4) { if (sub == 8) RNNT_LSE_LAUNCH(8, true); else RNNT_LSE_LAUNCH(32, true); }
+    else if (sub == 1) RNNT_LSE_LAUNCH(1, false);
+    else if (sub == 8) RNNT_LSE_LAUNCH(8, false);
+    else RNNT_LSE_LAUNCH(32, false);
+#undef RNNT_LSE_LAUNCH
     count_launch();
     return cudaGetLastError();
 }

@@ -147,7 +147,7 @@ k_gather(Problem p, const IO *__restrict__ lp, const int *__restrict__ labels, i
 // ------------------------------------------------------------------------------------------
 // k_wavefront
 // ------------------------------------------------------------------------------------------
-constexpr int kPrefetch = 8;   // steps of log-prob prefetch per register buffer (double-buffered)
+// kPrefetch (template parameter PF): steps of log-prob prefetch = unroll factor of the recurrence loop
 
 struct __align__(8) Slot { float val; int row; };
 
@@ -226,8 +226,9 @@ constexpr float kBig = -1.0e30f;
 //   cell (0,0): val starts at 0 with wB(0,0) = 0 (alpha) / blank[T-1,U-1] (beta)   (core.cu:64-66,171-173)
 //   i < 0     : wL = kBig, wB = 0           -> val stays kBig until the lane's first row
 //   i >= Tn   : results are garbage that no in-lattice cell ever reads; stores are masked.
-template <int KIND, bool BETA, int SRC>
+template <int KIND, bool BETA, int SRC, int PF>
 __device__ __forceinline__ float sweep_warp(const Sweep &S) {
+    constexpr int kPrefetch = PF;
     const int lane = S.lane, j = S.j, Tn = S.Tn, st = S.st, T1 = S.T1, U1 = S.U1;
     const unsigned rows = S.col_ok ? (unsigned)Tn : 0u;    // (unsigned)i < rows  <=>  cell (i,j) is in the lattice
     const bool first_col = (j == 0);
@@ -318,7 +319,7 @@ __device__ __forceinline__ float sweep_warp(const Sweep &S) {
     return last;
 }
 
-template <int KIND, bool BETA>
+template <int KIND, bool BETA, int PF>
 __device__ void wavefront_dir(const Lattice &L, const float2 *__restrict__ pairs, float *__restrict__ out,
                               Slot *ring, int ring_size, int *cons, float *ll_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -383,9 +384,9 @@ __device__ void wavefront_dir(const Lattice &L, const float2 *__restrict__ pairs
         }
 
         float val;
-        if (warp > 0) val = sweep_warp<KIND, BETA, kLeftRing>(S);
-        else if (col0 > 0 || col0_scan) val = sweep_warp<KIND, BETA, kLeftMem>(S);
-        else val = sweep_warp<KIND, BETA, kLeftNone>(S);
+        if (warp > 0) val = sweep_warp<KIND, BETA, kLeftRing, PF>(S);
+        else if (col0 > 0 || col0_scan) val = sweep_warp<KIND, BETA, kLeftMem, PF>(S);
+        else val = sweep_warp<KIND, BETA, kLeftNone, PF>(S);
 
         // the thread that owns the last cell reports the log-likelihood seen from this direction
         if (S.j == U1 && ll_out != nullptr) {
@@ -397,7 +398,7 @@ __device__ void wavefront_dir(const Lattice &L, const float2 *__restrict__ pairs
 
 // grid (2, N) with cluster (2,1,1): rank 0 = alpha, rank 1 = beta (beta_only: grid (1,N), no cluster).
 // ws_ll: (2,N) floats {alpha-side ll, beta-side ll}; bad: (N) ints (1 = mismatch guard fired).
-template <int KIND>
+template <int KIND, int PF>
 __global__ void __launch_bounds__(512, 1) k_wavefront(Problem p, const float2 *__restrict__ pairs,
                                                     float *__restrict__ alphas, float *__restrict__ betas,
                                                     float *__restrict__ ws_ll, int *__restrict__ bad,
@@ -412,8 +413,8 @@ __global__ void __launch_bounds__(512, 1) k_wavefront(Problem p, const float2 *_
     const Lattice L = get_lattice(p, n);
     float *ll = ws_ll + (is_beta ? p.N : 0) + n;
     if (L.ok) {
-        if (is_beta) wavefront_dir<KIND, true>(L, pairs, betas, ring, ring_size, cons, ll);
-        else wavefront_dir<KIND, false>(L, pairs, alphas, ring, ring_size, cons, ll);
+        if (is_beta) wavefront_dir<KIND, true, PF>(L, pairs, betas, ring, ring_size, cons, ll);
+        else wavefront_dir<KIND, false, PF>(L, pairs, alphas, ring, ring_size, cons, ll);
     }
     if (!beta_only) {
         // alpha and beta CTAs of a lattice meet here; release/acquire orders the ll writes.
@@ -523,10 +524,10 @@ cudaError_t launch_gather(cudaStream_t s, const Problem &p, const void *lp, cons
     return cudaGetLastError();
 }
 
-template <int KIND>
-static cudaError_t launch_wavefront_kind(cudaStream_t s, const Problem &p, const float2 *pairs, float *alphas,
-                                         float *betas, float *ws_ll, int *bad, float *costs, int beta_only,
-                                         int guard, int t_hint, int u_hint) {
+template <int KIND, int PF>
+static cudaError_t launch_wavefront_kp(cudaStream_t s, const Problem &p, const float2 *pairs, float *alphas,
+                                       float *betas, float *ws_ll, int *bad, float *costs, int beta_only,
+                                       int guard, int t_hint, int u_hint) {
     // warps per CTA: one per 32 lattice columns, at most 16 (more columns -> column passes)
     int nwarps = (u_hint > 0 ? u_hint + 31 : 512) / 32;
     nwarps = max(1, min(nwarps, 16));
@@ -538,7 +539,7 @@ static cudaError_t launch_wavefront_kind(cudaStream_t s, const Problem &p, const
     const size_t smem = sizeof(Slot) * (size_t)nwarps * ring + sizeof(int) * nwarps;
     static std::atomic<bool> attr_done[kMaxDevices];
     {
-        const cudaError_t e = ensure_dyn_smem(k_wavefront<KIND>, attr_done, 200 * 1024);
+        const cudaError_t e = ensure_dyn_smem(k_wavefront<KIND, PF>, attr_done, 200 * 1024);
         if (e != cudaSuccess) return e;
     }
     cudaLaunchConfig_t cfg = {};
@@ -554,8 +555,20 @@ static cudaError_t launch_wavefront_kind(cudaStream_t s, const Problem &p, const
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     count_launch();
-    return cudaLaunchKernelEx(&cfg, k_wavefront<KIND>, p, pairs, alphas, betas, ws_ll, bad, costs, beta_only, guard,
+    return cudaLaunchKernelEx(&cfg, k_wavefront<KIND, PF>, p, pairs, alphas, betas, ws_ll, bad, costs, beta_only, guard,
                               ring, guard_poison());
+}
+
+// The unroll factor of the recurrence loop = its operand prefetch distance.  The exact-LSE body is ~150 instructions
+// per step; unrolled 8x, the two instantiations a CTA runs (ring-fed warps + the column-0 warp) are ~40 KB of SASS,
+// more than the 32 KB instruction cache behind an SM's schedulers (ncu r1: "no instruction" was the top stall reason).
+// Measured at cfg 4 (us): exact 1027 / 797 / 986 for unroll 8 / 4 / 2, fast 634 / 687 / 855 -> 4 for exact, 8 for fast.
+template <int KIND>
+static cudaError_t launch_wavefront_kind(cudaStream_t s, const Problem &p, const float2 *pairs, float *alphas,
+                                         float *betas, float *ws_ll, int *bad, float *costs, int beta_only,
+                                         int guard, int t_hint, int u_hint) {
+    constexpr int PF = (KIND == kFast) ? 8 : 4;
+    return launch_wavefront_kp<KIND, PF>(s, p, pairs, alphas, betas, ws_ll, bad, costs, beta_only, guard, t_hint, u_hint);
 }
 
 cudaError_t launch_wavefront(cudaStream_t s, int kind, const Problem &p, const float2 *pairs, float *alphas,
