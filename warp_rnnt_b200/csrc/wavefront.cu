@@ -206,7 +206,6 @@ struct Sweep {
     int j, lane;
     int nsteps, ring_mask;
     bool col_ok, publish, backpressure, override0;
-    bool steady;        // use the predicate-free steady-state block (RNNT_B200_STEADY=0 disables it)
 };
 
 // "Minus infinity" that stays finite: cells outside the lattice carry kBig so that the one uniform
@@ -214,11 +213,6 @@ struct Sweep {
 // absorbed) exactly, in every LSE flavour, and kBig + (any log-prob) stays ~kBig without ever
 // producing inf - inf.
 constexpr float kBig = -1.0e30f;
-
-// (wb, wl) = (0, kBig) in global memory: where the steady-state block of sweep_warp points the operand loads of lanes
-// that have nothing to load (columns past the lattice, the first column's missing label edge), so that its loads
-// need no predicates.
-__device__ const float g_sentinel[2] = {0.0f, kBig};
 
 // One direction of one lattice.  "Primed" coordinates (i,j): alpha uses (t,u); beta uses
 // (Tn-1-t, Un-1-u), so both are the same recurrence
@@ -293,54 +287,7 @@ __device__ __forceinline__ float sweep_warp(const Sweep &S) {
     for (int k = 0; k < kPrefetch; ++k) fetch(k, k);
 
     float *op = S.o + c0;
-    // Steady state: a block of kPrefetch steps in which every lane's row -- for the step itself and for the operands it
-    // prefetches kPrefetch steps ahead -- lies inside the lattice.  There the loads need no row predicates, the store
-    // and ring tests are loop-invariant and the addresses advance by pointer increments: ~65 instructions per step
-    // instead of ~150 in the general block below (which handles the ramp-up / ramp-down triangles at both ends).
-    // Small code matters as much as few instructions here: the loop is instruction-fetch bound (see launch_wavefront_kind).
-    const float *base_wb = reinterpret_cast<const float *>(S.pr + c0) - (BETA ? 0 : 2 * (int64_t)st);
-    const float *base_wl = reinterpret_cast<const float *>(S.pr + c0) + (BETA ? 1 : -1);
-    const bool lane_ok = S.col_ok;
-    const bool wl_ok = lane_ok && !first_col;
-    const int64_t dsb = lane_ok ? 2 * ds : 0, dsl = wl_ok ? 2 * ds : 0, dsm = mem_lane ? ds : 0;
     for (int s0 = 0; s0 < S.nsteps; s0 += kPrefetch) {
-        if (S.steady && s0 >= 32 && s0 + 2 * kPrefetch <= Tn) {
-            const float *pwb = lane_ok ? base_wb + (int64_t)(s0 + kPrefetch) * dsb : g_sentinel;
-            const float *pwl = wl_ok ? base_wl + (int64_t)(s0 + kPrefetch) * dsl : g_sentinel + 1;
-            const float *pbd = mem_lane ? S.o + c0 + (int64_t)(s0 + kPrefetch) * ds + bcol : g_sentinel;
-#pragma unroll
-            for (int k = 0; k < kPrefetch; ++k) {
-                const int s = s0 + k;
-                float left = __shfl_up_sync(0xffffffffu, val, 1);
-                if (SRC == kLeftRing) {
-                    const float b = ring_get(s);
-                    if (lane == 0) left = b;
-                } else if (SRC == kLeftMem) {
-                    if (lane == 0) left = bnd[k];
-                }
-                float v = lse<KIND>(val + wb[k], left + wl[k]);
-                if (SRC == kLeftMem) {
-                    if (S.override0 && lane == 0) v = bnd[k];      // column 0 from the scan pre-pass
-                }
-                val = v;
-                if (lane_ok) {
-                    *op = v;
-                    last = v;
-                }
-                op += ds;
-                if (S.publish) ring_put(s - 31, v);
-                // volatile: the loads stay HERE, kPrefetch steps ahead of their use
-                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(wb[k]) : "l"(pwb));
-                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(wl[k]) : "l"(pwl));
-                pwb += dsb;
-                pwl += dsl;
-                if (SRC == kLeftMem) {
-                    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(bnd[k]) : "l"(pbd) : "memory");
-                    pbd += dsm;
-                }
-            }
-            continue;
-        }
 #pragma unroll
         for (int k = 0; k < kPrefetch; ++k) {
             const int s = s0 + k;                               // steps past nsteps are harmless no-ops
@@ -374,7 +321,7 @@ __device__ __forceinline__ float sweep_warp(const Sweep &S) {
 
 template <int KIND, bool BETA, int PF>
 __device__ void wavefront_dir(const Lattice &L, const float2 *__restrict__ pairs, float *__restrict__ out,
-                              Slot *ring, int ring_size, int *cons, float *ll_out, int steady) {
+                              Slot *ring, int ring_size, int *cons, float *ll_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int Tn = L.Tn, Un = L.Un, st = L.stride;
     const int T1 = Tn - 1, U1 = Un - 1;
@@ -411,7 +358,6 @@ __device__ void wavefront_dir(const Lattice &L, const float2 *__restrict__ pairs
         S.ring_mask = ring_size - 1;
         S.backpressure = Tn > ring_size;
         S.override0 = false;
-        S.steady = steady != 0;
 
         // Exact mode, column 0: the reference builds it with a 32-wide Kogge-Stone scan per tile
         // plus the tile's base value (core.cu:92-110 / :197-215); reproduce that summation order
@@ -457,7 +403,7 @@ __global__ void __launch_bounds__(512, 1) k_wavefront(Problem p, const float2 *_
                                                     float *__restrict__ alphas, float *__restrict__ betas,
                                                     float *__restrict__ ws_ll, int *__restrict__ bad,
                                                     float *__restrict__ costs, int beta_only, int guard, int ring_size,
-                                                    GuardPoison poison, int steady) {
+                                                    GuardPoison poison) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nwarps = blockDim.x >> 5;
     Slot *ring = reinterpret_cast<Slot *>(smem_raw);
@@ -467,8 +413,8 @@ __global__ void __launch_bounds__(512, 1) k_wavefront(Problem p, const float2 *_
     const Lattice L = get_lattice(p, n);
     float *ll = ws_ll + (is_beta ? p.N : 0) + n;
     if (L.ok) {
-        if (is_beta) wavefront_dir<KIND, true, PF>(L, pairs, betas, ring, ring_size, cons, ll, steady);
-        else wavefront_dir<KIND, false, PF>(L, pairs, alphas, ring, ring_size, cons, ll, steady);
+        if (is_beta) wavefront_dir<KIND, true, PF>(L, pairs, betas, ring, ring_size, cons, ll);
+        else wavefront_dir<KIND, false, PF>(L, pairs, alphas, ring, ring_size, cons, ll);
     }
     if (!beta_only) {
         // alpha and beta CTAs of a lattice meet here; release/acquire orders the ll writes.
@@ -596,7 +542,6 @@ static cudaError_t launch_wavefront_kp(cudaStream_t s, const Problem &p, const f
         const cudaError_t e = ensure_dyn_smem(k_wavefront<KIND, PF>, attr_done, 200 * 1024);
         if (e != cudaSuccess) return e;
     }
-    static const int steady = env_int("RNNT_B200_STEADY", 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(beta_only ? 1 : 2, p.N, 1);
     cfg.blockDim = dim3(32 * nwarps, 1, 1);
@@ -611,7 +556,7 @@ static cudaError_t launch_wavefront_kp(cudaStream_t s, const Problem &p, const f
     cfg.numAttrs = 1;
     count_launch();
     return cudaLaunchKernelEx(&cfg, k_wavefront<KIND, PF>, p, pairs, alphas, betas, ws_ll, bad, costs, beta_only, guard,
-                              ring, guard_poison(), steady);
+                              ring, guard_poison());
 }
 
 // The unroll factor of the recurrence loop = its operand prefetch distance.  The exact-LSE body is ~150 instructions
