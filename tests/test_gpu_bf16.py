@@ -28,10 +28,11 @@ def cu(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-# fused kernel (TMA rows / LDG gather / several CTAs per lattice) and general path (serial and pipelined)
+# fused kernel (TMA rows / LDG gather / several CTAs per lattice) and general path (serial; the last one pipelined:
+# its emit is long against its wavefront, see api.cu)
 SHAPES = [(3, 20, 9, 8, True, 0, 0.0), (4, 150, 40, 28, True, 0, 0.0), (2, 33, 34, 5, True, 2, 0.25),
           (3, 40, 12, 1000, False, 0, 0.0), (2, 700, 40, 6, True, 0, 0.0), (2, 300, 50, 50, True, 0, 0.1),
-          (8, 600, 150, 200, True, 0, 0.0)]
+          (32, 300, 70, 1200, True, 0, 0.0)]
 
 
 @pytest.mark.parametrize("mode", ["exact", "fast"])

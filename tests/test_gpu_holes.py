@@ -1,8 +1,8 @@
 """GPU: the code paths round 1 left without an oracle / reference comparison ("what's weak" 1-3).
 
   * BASELINE cfg 4 (N=64 T=1500 U=300 V=50, random lengths) in EXACT mode, dense and compact=True, against the
-    fp64 oracle on 8 lattices and bit-for-bit against the compiled reference on 2 lattices -- with the 8-group
-    multi-stream pipeline of the general path active (it needs the full batch);
+    fp64 oracle on 8 lattices and bit-for-bit against the compiled reference on 2 lattices; the 8-group multi-stream
+    pipeline of the general path on a shape that takes it;
   * ring back-pressure in k_wavefront (a lattice longer than the boundary ring, and the compact C ABI without
     max_T / max_U hints);
   * the forward/backward mismatch guard's FIRED branch (core.cu:349-367) through a test-only hook;
@@ -83,7 +83,7 @@ def test_cfg4_exact_dense_and_compact_vs_oracle_and_reference(w, ref):
     xs, ys, xn, yn = synth(N, T, U, V, seed=64)
     w.set_lse_mode("exact")
     try:
-        costs, grads = w._C.rnnt_loss(xs, ys, xn, yn)              # full batch: the 8-group pipeline is active
+        costs, grads = w._C.rnnt_loss(xs, ys, xn, yn)              # full batch (serial general path: see the pipeline test)
         assert torch.isfinite(costs).all()
         pick = [0, 7, 8, 21, 33, 40, 55, 63]                        # lattices from different pipeline groups
         sel = torch.tensor(pick, device="cuda")
@@ -145,6 +145,31 @@ def test_cfg4_exact_dense_and_compact_vs_oracle_and_reference(w, ref):
                 assert torch.equal(cc[i], cm[two.index(i)])
                 assert torch.equal(pg[s:s + c], gm[o:o + c])
                 o += c
+    finally:
+        w.set_lse_mode("auto")
+
+
+# ------------------------------------------------------------------------------------------ the stream pipeline
+def test_pipelined_general_path_vs_oracle_and_reference(w, ref):
+    """N=32 T=300 U=70 V=1200: too large for the fused kernel, and the emit (3.2 GB) is long against the wavefront, so
+    rnnt_b200_loss_dense runs its 8-group multi-stream pipeline (api.cu).  cfg 4 itself takes the serial path since
+    round 2 (its wavefront is as long as its emit)."""
+    N, T, U, V = 32, 300, 70, 1200
+    xs, ys, xn, yn = synth(N, T, U, V, seed=32)
+    w.set_lse_mode("exact")
+    try:
+        n0 = w._C.launch_count()
+        costs, grads = w._C.rnnt_loss(xs, ys, xn, yn)
+        assert w._C.launch_count() - n0 == 24                        # 8 groups x (gather, wavefront, emit)
+        pick = [0, 5, 17, 31]
+        sel = torch.tensor(pick, device="cuda")
+        c0, g0 = oracle.dense(xs[sel].cpu().numpy(), ys[sel].cpu().numpy(), xn[sel].cpu().numpy(), yn[sel].cpu().numpy())
+        np.testing.assert_allclose(costs[sel].cpu().numpy(), c0, rtol=1e-5)
+        assert np.abs(grads[sel].cpu().numpy() - g0).max() <= gtol(T, U)
+        if ref is not None:
+            two = torch.tensor([5, 31], device="cuda")
+            cr, gr = ref.rnnt_loss(xs[two].contiguous(), ys[two].contiguous(), xn[two].contiguous(), yn[two].contiguous())
+            assert torch.equal(costs[two], cr) and torch.equal(grads[two], gr)
     finally:
         w.set_lse_mode("auto")
 
@@ -244,7 +269,7 @@ def test_two_devices_in_one_process(w):
     """cuda:0 first, then cuda:1, same process: function attributes / occupancy / pipeline streams are per device."""
     shapes = [(5, 150, 40, 28, "fused, > 48 KB dynamic shared memory"),
               (3, 300, 600, 4, "general path, > 48 KB ring"),
-              (8, 600, 150, 200, "general path, multi-stream pipeline (576 MB of gradients)"),
+              (32, 300, 70, 1200, "general path, multi-stream pipeline (3.2 GB of gradients, short wavefront)"),
               (40, 30, 20, 4096, "fused, several CTAs per lattice (occupancy cache)")]
     w.set_lse_mode("exact")
     try:

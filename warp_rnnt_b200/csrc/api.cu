@@ -189,7 +189,12 @@ static int loss_dense_any(void *stream, void *workspace, size_t workspace_bytes,
     const int kind = resolve_kind(lse_mode, false);
     // Large batches of large lattices: software-pipeline lattice groups over internal streams so that the
     // latency-bound wavefront of group g overlaps the bandwidth-bound gather of g+1 and emit of g-1.
-    const int groups = (grads && N >= 8 && (int64_t)cells * V * 4 >= ((int64_t)512 << 20) && pipeline_enabled())
+    // ... which only pays when the wavefront (a per-lattice latency chain of T+U-1 steps, ~0.45 us each, that does not
+    // shrink with the group) is short against the bandwidth-bound emit: measured on B200, cfg 5 micro-batch (chain
+    // 0.34 ms, emit 2.1 ms) 2.14 ms pipelined vs 2.39 ms serial; cfg 4 (chain 0.8 ms, emit 1.05 ms) 2.96 vs 2.70 ms.
+    const double wave_us = 0.45 * (T + U), emit_us = (double)cells * V * (io_bf16 ? 2 : 4) / 5.5e6;
+    const int groups = (grads && N >= 8 && (int64_t)cells * V * 4 >= ((int64_t)512 << 20) && pipeline_enabled() &&
+                        wave_us < 0.4 * emit_us)
                            ? (N >= 32 ? 8 : 4) : 1;
     if (groups > 1) {
         std::lock_guard<std::mutex> lock(g_pipe_mu);    // the pipeline's events are shared by all calls on this device
