@@ -190,6 +190,21 @@ int rnnt_b200_compact_forward(void *stream, void *workspace, size_t workspace_by
 int rnnt_b200_compact_totals(void *stream, const int *xn, const int *yn, int N, int64_t *scratch,
                              int *totals);
 
+/* Compact packing of the joint network's INPUT -- the caller side of the compact layout (SURVEY.md 8(f)3;
+ * the reference's benchmark does it with a python loop, 2N host syncs and a cat, benchmark2.py:37-50):
+ *   x[row(n,t,u), :] = f[n,t,:] + g[n,u,:]   for t < lf[n], u <= lg[n],   row(n,t,u) = mem_pref[n] + t*(lg[n]+1) + u
+ * f (N,T,H) encoder output, g (N,U1,H) predictor output (U1 = max labels + 1), lf / lg (N) i32 = the loss'
+ * frames_lengths / labels_lengths, x (STU,H) out, H the joint dimension.  scratch: 2*N int64 of device memory; on
+ * return scratch[0..N) = mem_pref (kept by the caller for the backward).  totals (4) i32 out or NULL as in
+ * rnnt_b200_compact_totals (totals[0] = STU).  x == NULL: prefix sums / totals only (to size x).
+ * stu_hint: STU if known (launch shaping only), else 0. */
+int rnnt_b200_joint_pack(void *stream, const float *f, const float *g, const int *lf, const int *lg,
+                         int64_t *scratch, int *totals, float *x, int N, int T, int U1, int H, int64_t stu_hint);
+/* ... and its backward: df (N,T,H) = sum over u of dx rows, dg (N,U1,H) = sum over t; zeros on padding; fixed
+ * summation order (deterministic).  df or dg may be NULL. */
+int rnnt_b200_joint_pack_backward(void *stream, const float *dx, const int *lf, const int *lg,
+                                  const int64_t *mem_pref, float *df, float *dg, int N, int T, int U1, int H);
+
 /* Compact backward: out (STU,V) fully written.  Replaces torch::zeros (binding.cpp:239) +
  * run_scatter_grad_for_compact (core.h:56-60).  cum_lens (N) i32 inclusive cumsum. */
 int rnnt_b200_compact_backward(void *stream, const float *grad_cost, const float *pair_grads,

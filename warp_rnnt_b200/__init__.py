@@ -29,13 +29,16 @@ _LIB_PATH = os.path.join(_HERE, "lib", "librnnt_b200.so")
 
 
 def _load_ext():
-    if not (os.path.exists(_EXT_PATH) and os.path.exists(_LIB_PATH)):
+    # Stale binaries must not load silently: lib/sources.sha256 records the content hash of the sources the two
+    # artefacts were built from; on a mismatch (edited sources, a pull) they are rebuilt -- or, with
+    # RNNT_B200_NO_AUTOBUILD=1, the import fails.
+    from . import build as _build
+    if not _build.up_to_date():
         if os.environ.get("RNNT_B200_NO_AUTOBUILD") == "1":
             raise ImportError(
-                "warp_rnnt_b200: the CUDA extension is not built (%s missing). "
+                "warp_rnnt_b200: the CUDA extension is missing or older than its sources (%s). "
                 "Run `python -m warp_rnnt_b200.build`; there is no CPU fallback." % _EXT_PATH)
-        from . import build as _build        # builds the CUDA extension itself (nvcc + g++)
-        _build.build_all()
+        _build.build_all()                   # builds the CUDA extension itself (nvcc + g++)
     name = __name__ + "._C"
     loader = importlib.machinery.ExtensionFileLoader(name, _EXT_PATH)
     spec = importlib.util.spec_from_file_location(name, _EXT_PATH, loader=loader)
@@ -174,6 +177,32 @@ def rnnt_loss_from_logits(logits, labels, frames_lengths, labels_lengths, averag
     return costs
 
 
+class JointPack(torch.autograd.Function):
+    """x[(n,t,u), :] = f[n,t,:] + g[n,u,:] in the compact (ragged) row order that ``rnnt_loss(compact=True)`` takes --
+    the joint network's input without padding (the reference's benchmark2.py:37-50 builds it with a python loop over
+    the batch).  One kernel forward, two deterministic reductions backward."""
+
+    @staticmethod
+    def forward(ctx, f, g, lf, lg, stu=-1):
+        x, mem_pref = _C.rnnt_joint_pack(f.contiguous(), g.contiguous(), lf, lg, int(stu))
+        ctx.save_for_backward(lf, lg, mem_pref)
+        ctx.shape = (f.size(1), g.size(1))
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        lf, lg, mem_pref = ctx.saved_tensors
+        df, dg = _C.rnnt_joint_pack_backward(dx.contiguous().float(), lf, lg, mem_pref, ctx.shape[0], ctx.shape[1])
+        return df, dg, None, None, None
+
+
+def joint_pack(f, g, frames_lengths, labels_lengths, stu=None):
+    """f (N,T,H) encoder output, g (N,U+1,H) predictor output -> (STU,H), STU = sum frames_lengths*(labels_lengths+1):
+    the packed input of the joint network whose (STU,V) log-softmax output goes to ``rnnt_loss(..., compact=True)``.
+    ``stu``: pass STU when known to avoid the one device->host copy that sizes the output."""
+    return JointPack.apply(f, g, frames_lengths, labels_lengths, -1 if stu is None else int(stu))
+
+
 class RNNTLossEager(torch.autograd.Function):
     """Reference-shaped variant: dense gradients are produced in forward (one fused pass) and
     scaled in backward, exactly like the reference's RNNTLoss (__init__.py:11-24)."""
@@ -298,5 +327,5 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=
             f"Unknown reduction method: {reduction}, expected to be one of ['mean', 'sum', 'none']")
 
 
-__all__ = ["rnnt_loss", "rnnt_loss_from_logits", "RNNTLossFromLogits", "RNNTLoss", "RNNTLossGather", "RNNTLossEager", "RNNTLossCompact", "compact_hints", "set_lse_mode", "core", "_C",
+__all__ = ["rnnt_loss", "rnnt_loss_from_logits", "joint_pack", "JointPack", "RNNTLossFromLogits", "RNNTLoss", "RNNTLossGather", "RNNTLossEager", "RNNTLossCompact", "compact_hints", "set_lse_mode", "core", "_C",
            "__version__"]

@@ -21,7 +21,7 @@ LIB = os.path.join(LIBDIR, "librnnt_b200.so")
 EXT = os.path.join(LIBDIR, "_C.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-CU_SOURCES = ["wavefront.cu", "expand.cu", "fused.cu", "logits.cu", "api.cu"]
+CU_SOURCES = ["wavefront.cu", "expand.cu", "fused.cu", "logits.cu", "joint.cu", "api.cu"]
 CU_HEADERS = ["common.cuh", "kernels.cuh", os.path.join(INCLUDE, "rnnt_b200.h")]
 
 
@@ -32,6 +32,36 @@ def _nvcc():
     raise RuntimeError("nvcc not found: the CUDA extension cannot be built (there is no CPU fallback)")
 
 
+def cu_sources():
+    return [os.path.join(CSRC, s) for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+STAMP = os.path.join(LIBDIR, "sources.sha256")
+
+
+def sources_digest():
+    """Content hash of everything the two artefacts are built from (mtimes do not survive copies to another box)."""
+    import hashlib
+    h = hashlib.sha256()
+    files = cu_sources() + [d if os.path.isabs(d) else os.path.join(CSRC, d) for d in CU_HEADERS] + \
+        [os.path.join(CSRC, "binding.cpp")]
+    for f in sorted(files):
+        if os.path.exists(f):
+            h.update(os.path.basename(f).encode())
+            h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
+def up_to_date():
+    """True when lib/ holds both artefacts AND they were built from the sources as they are now."""
+    if not (os.path.exists(LIB) and os.path.exists(EXT) and os.path.exists(STAMP)):
+        return False
+    try:
+        return open(STAMP).read().strip() == sources_digest()
+    except OSError:
+        return False
+
+
 def _stale(target, deps):
     if not os.path.exists(target):
         return True
@@ -39,8 +69,6 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def cu_sources():
-    return [os.path.join(CSRC, s) for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
 def build_lib(force=False, verbose=False):
@@ -84,8 +112,11 @@ def build_ext(force=False):
 
 
 def build_all(force=False, verbose=False):
+    force = force or not up_to_date()
     build_lib(force, verbose)
     build_ext(force)
+    with open(STAMP, "w") as f:
+        f.write(sources_digest() + "\n")
     return LIB, EXT
 
 

@@ -484,6 +484,26 @@ int rnnt_b200_compact_totals(void *stream, const int *xn, const int *yn, int N, 
     return RNNT_STATUS_SUCCESS;
 }
 
+int rnnt_b200_joint_pack(void *stream, const float *f, const float *g, const int *lf, const int *lg, int64_t *scratch,
+                         int *totals, float *x, int N, int T, int U1, int H, int64_t stu_hint) {
+    if (N < 0 || T < 1 || U1 < 1 || H < 1 || !scratch) return RNNT_STATUS_INVALID_ARGUMENT;
+    if (N == 0) return RNNT_STATUS_SUCCESS;
+    cudaStream_t s = (cudaStream_t)stream;
+    // mem_pref[n] = first packed row of lattice n: the same device prefix sums as the compact loss (lf = xn, lg = yn)
+    RNNT_TRY(launch_prefix(s, lf, lg, N, scratch, scratch + N, totals), RNNT_STATUS_GATHER_FAILED);
+    if (x) RNNT_TRY(launch_joint_pack(s, f, g, lf, lg, scratch, x, N, T, U1, H, stu_hint), RNNT_STATUS_GATHER_FAILED);
+    return RNNT_STATUS_SUCCESS;
+}
+
+int rnnt_b200_joint_pack_backward(void *stream, const float *dx, const int *lf, const int *lg, const int64_t *mem_pref,
+                                  float *df, float *dg, int N, int T, int U1, int H) {
+    if (N < 0 || T < 1 || U1 < 1 || H < 1 || !mem_pref || !dx) return RNNT_STATUS_INVALID_ARGUMENT;
+    if (N == 0) return RNNT_STATUS_SUCCESS;
+    RNNT_TRY(launch_joint_grads((cudaStream_t)stream, dx, lf, lg, mem_pref, df, dg, N, T, U1, H),
+             RNNT_STATUS_GRADS_BLANK_FAILED);
+    return RNNT_STATUS_SUCCESS;
+}
+
 int rnnt_b200_compact_backward(void *stream, const float *grad_cost, const float *pair_grads, const int64_t *loc,
                                const int *cum_lens, float *out, int64_t STU, int N, int V, int blank) {
     if (N < 0 || STU < 0 || V < 1 || V >= (1 << 22) || blank < 0 || blank >= V) return RNNT_STATUS_INVALID_ARGUMENT;

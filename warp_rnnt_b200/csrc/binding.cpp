@@ -10,6 +10,7 @@
 // element); compact shapes are validated with one small device->host copy instead of four .item()s.
 // Extra entry points (rnnt_loss_dense, rnnt_gather_forward/backward) serve the fused python-level
 // paths of warp_rnnt_b200/__init__.py.
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <tuple>
@@ -328,6 +329,61 @@ at::Tensor rnnt_logits_backward(const at::Tensor &xs, const at::Tensor &lse, con
     return out;
 }
 
+// compact packing of the joint input: (x (STU,H), mem_pref (N) int64).  stu < 0: STU is read back from the device
+// (one 16-byte copy); stu >= 0: trusted, no host sync.
+std::tuple<at::Tensor, at::Tensor> rnnt_joint_pack(const at::Tensor &f, const at::Tensor &g, const at::Tensor &lf,
+                                                   const at::Tensor &lg, int64_t stu) {
+    TORCH_CHECK(f.is_contiguous() && g.is_contiguous() && lf.is_contiguous() && lg.is_contiguous(), "inputs must be contiguous");
+    TORCH_CHECK(f.scalar_type() == at::ScalarType::Float && g.scalar_type() == at::ScalarType::Float,
+                "f and g must be Float tensors");
+    TORCH_CHECK(lf.scalar_type() == at::ScalarType::Int && lg.scalar_type() == at::ScalarType::Int,
+                "lf and lg must be Int tensors");
+    TORCH_CHECK(f.device().is_cuda() && g.device() == f.device() && lf.device() == f.device() && lg.device() == f.device(),
+                "f, g, lf, lg must be on the same CUDA device");
+    TORCH_CHECK(f.dim() == 3 && g.dim() == 3 && f.size(0) == g.size(0) && f.size(2) == g.size(2),
+                "f must be (N, T, H) and g (N, U+1, H)");
+    const int64_t N = f.size(0), T = f.size(1), U1 = g.size(1), H = f.size(2);
+    TORCH_CHECK(lf.numel() == N && lg.numel() == N, "lf and lg must have N elements");
+    const c10::cuda::CUDAGuard guard(f.device());
+    void *stream = current_stream(f);
+    at::Tensor scratch = at::empty({2 * std::max<int64_t>(N, 1)}, f.options().dtype(at::kLong));
+    if (N == 0) return std::make_tuple(at::empty({0, H}, f.options()), scratch);
+    if (stu < 0) {
+        at::Tensor totals = at::empty({4}, f.options().dtype(at::kInt));
+        check_status(rnnt_b200_joint_pack(stream, nullptr, nullptr, lf.data_ptr<int>(), lg.data_ptr<int>(),
+                                          scratch.data_ptr<int64_t>(), totals.data_ptr<int>(), nullptr, (int)N, (int)T,
+                                          (int)U1, (int)H, 0));
+        at::Tensor h = totals.cpu();
+        const int *t = h.data_ptr<int>();
+        TORCH_CHECK(t[2] <= T && t[3] <= U1, "lf / lg exceed the shapes of f / g");
+        stu = t[0];
+    }
+    at::Tensor x = at::empty({stu, H}, f.options());
+    check_status(rnnt_b200_joint_pack(stream, f.data_ptr<float>(), g.data_ptr<float>(), lf.data_ptr<int>(),
+                                      lg.data_ptr<int>(), scratch.data_ptr<int64_t>(), nullptr, x.data_ptr<float>(), (int)N,
+                                      (int)T, (int)U1, (int)H, stu));
+    return std::make_tuple(x, scratch.narrow(0, 0, N));
+}
+
+std::tuple<at::Tensor, at::Tensor> rnnt_joint_pack_backward(const at::Tensor &dx, const at::Tensor &lf,
+                                                            const at::Tensor &lg, const at::Tensor &mem_pref,
+                                                            int64_t T, int64_t U1) {
+    TORCH_CHECK(dx.is_contiguous() && dx.scalar_type() == at::ScalarType::Float && dx.device().is_cuda() && dx.dim() == 2,
+                "dx must be a contiguous CUDA Float tensor of shape (STU, H)");
+    TORCH_CHECK(mem_pref.is_contiguous() && mem_pref.scalar_type() == at::ScalarType::Long && mem_pref.device() == dx.device(),
+                "mem_pref must be a contiguous Long tensor on the device of dx");
+    const int64_t N = mem_pref.numel(), H = dx.size(1);
+    TORCH_CHECK(lf.numel() == N && lg.numel() == N && lf.is_contiguous() && lg.is_contiguous() &&
+                    lf.scalar_type() == at::ScalarType::Int && lg.scalar_type() == at::ScalarType::Int,
+                "lf and lg must be contiguous Int tensors with N elements");
+    const c10::cuda::CUDAGuard guard(dx.device());
+    at::Tensor df = at::empty({N, T, H}, dx.options()), dg = at::empty({N, U1, H}, dx.options());
+    check_status(rnnt_b200_joint_pack_backward(current_stream(dx), dx.data_ptr<float>(), lf.data_ptr<int>(),
+                                               lg.data_ptr<int>(), mem_pref.data_ptr<int64_t>(), df.data_ptr<float>(),
+                                               dg.data_ptr<float>(), (int)N, (int)T, (int)U1, (int)H));
+    return std::make_tuple(df, dg);
+}
+
 at::Tensor rnnt_gather_backward(const at::Tensor &pair_grads, const at::Tensor &ys, const at::Tensor &grad_out,
                                 int64_t V, int blank, bool accumulate) {
     TORCH_CHECK(pair_grads.is_contiguous() && pair_grads.scalar_type() == at::ScalarType::Float &&
@@ -372,6 +428,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("blank") = 0, py::arg("fastemit_lambda") = 0.0, py::arg("want_grads") = true, py::arg("lse_mode") = 0);
     m.def("rnnt_logits_backward", &rnnt_logits_backward, py::arg("xs"), py::arg("lse"), py::arg("pair_grads"),
           py::arg("ys"), py::arg("grad_out"), py::arg("blank") = 0);
+    m.def("rnnt_joint_pack", &rnnt_joint_pack, py::arg("f"), py::arg("g"), py::arg("lf"), py::arg("lg"), py::arg("stu") = -1);
+    m.def("rnnt_joint_pack_backward", &rnnt_joint_pack_backward, py::arg("dx"), py::arg("lf"), py::arg("lg"),
+          py::arg("mem_pref"), py::arg("T"), py::arg("U1"));
     m.def("rnnt_gather_forward", &rnnt_gather_forward, py::arg("xs"), py::arg("ys"), py::arg("xn"), py::arg("yn"),
           py::arg("blank") = 0, py::arg("fastemit_lambda") = 0.0, py::arg("want_grads") = true,
           py::arg("lse_mode") = 0);

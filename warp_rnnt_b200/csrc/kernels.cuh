@@ -46,6 +46,12 @@ cudaError_t launch_lse_pairs(cudaStream_t s, const float *x, const int *labels, 
 cudaError_t launch_expand_logits(cudaStream_t s, const float *x, const float *lse, const float2 *pg, const int *labels,
                                  const float *grad_out, float *out, int N, int T, int U, int V, int blank);
 
+// joint.cu -- compact packing of the joint network's input (caller side of compact=True)
+cudaError_t launch_joint_pack(cudaStream_t s, const float *f, const float *g, const int *lf, const int *lg,
+                              const int64_t *mem_pref, float *x, int N, int T, int U1, int H, int64_t stu_hint);
+cudaError_t launch_joint_grads(cudaStream_t s, const float *dx, const int *lf, const int *lg, const int64_t *mem_pref,
+                               float *df, float *dg, int N, int T, int U1, int H);
+
 // fused.cu -- single-kernel path for lattices that fit shared memory
 struct FusedPlan { int W, ring, nw, slices; size_t smem; };
 bool fused_plan(int N, int T, int U, FusedPlan *plan);
