@@ -1,28 +1,33 @@
 #!/bin/bash
 # Round-end evidence on one B200 (run through gpurun): tests on every kernel path, smoke, bench lines for all
 # workloads (+ the reference arm with REF=1), ncu launch lists and full captures (c4 with C4=1), fused-kernel
-# phase timelines.  Outputs under gpurun_out/ev/ ; summarised into profiles/ by tools/ncu_summary.py afterwards.
+# phase timelines, compute-sanitizer.  Outputs under gpurun_out/ev/ ; copied / summarised into profiles/ afterwards
+# (tools/ncu_summary.py, tools/collect_profiles.py).
 set -u
 O=gpurun_out/ev; mkdir -p $O
 {
 echo "== pytest -m gpu (default paths)";            timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -3
-echo "== pytest -m gpu, RNNT_B200_PATH=general";    RNNT_B200_PATH=general timeout 600 python -m pytest tests -q -m gpu 2>&1 | tail -2
-echo "== pytest parity, LDG gather + STG fill";     RNNT_B200_GATHER=ldg RNNT_B200_FILL=stg timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_cabi.py -q -m gpu 2>&1 | tail -2
+echo "== pytest -m gpu, RNNT_B200_PATH=general";    RNNT_B200_PATH=general timeout 900 python -m pytest tests -q -m gpu --deselect tests/test_gpu_parity.py::test_python_api_one_launch_and_upstream_scaling 2>&1 | tail -2
+echo "== pytest parity, LDG gather + STG fill";     RNNT_B200_GATHER=ldg RNNT_B200_FILL=stg timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_cabi.py tests/test_gpu_bf16.py -q -m gpu 2>&1 | tail -2
+echo "== pytest parity, one row buffer per gather warp"; RNNT_B200_ROW_BUFS=1 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_bf16.py -q -m gpu 2>&1 | tail -2
 echo "== pytest parity, RNNT_B200_LSE=fast";        RNNT_B200_LSE=fast timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu 2>&1 | tail -2
 echo "== smoke";                                    python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+echo "== synccheck";                                timeout 300 compute-sanitizer --tool synccheck python -m pytest tests/test_gpu_parity.py -q -m gpu -k "golden_dense or dense_vs_oracle" 2>&1 | tail -3
 } > $O/tests.log 2>&1
 python bench.py --steps 100 --warmup 10 > $O/bench_c2.json 2> $O/bench_c2.err
 if [ "${REF:-0}" = 1 ]; then python bench.py --impl reference --steps 5 --warmup 3 > $O/bench_c2_reference.json 2> $O/bench_c2_reference.err; fi
-for w in c3 c4 c5mb; do python bench.py --workload $w --steps 20 --warmup 5 > $O/bench_$w.json 2> $O/bench_$w.err; done
+for w in c2g c3 c3d c4 c4d c5mb c2b c5mbb c2l; do timeout 400 python bench.py --workload $w --steps 20 --warmup 5 > $O/bench_$w.json 2> $O/bench_$w.err; done
 python tools/fused_timeline.py c2 $O/timeline_c2.json > $O/timeline_c2.log 2>&1
 python tools/fused_timeline.py c3 $O/timeline_c3.json > $O/timeline_c3.log 2>&1
-python tools/compact_time.py > $O/compact_time.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/launches_bench_c2.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_fused -s 2 -c 1 -f -o $O/fused_c2 python tools/one_call.py c2 exact > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_fused -s 2 -c 1 -f -o $O/fused_c3 python tools/one_call.py c3 exact > /dev/null 2>&1
+# launch lists: the API step as the bench runs it (eager, so that ncu sees every launch), cold-cache + serialised: shares only
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/launches_bench_c2.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --e2e-steps 1 > /dev/null 2>&1
 if [ "${C4:-0}" = 1 ]; then
-RNNT_B200_PIPELINE=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $O/launches_bench_c4.csv python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-RNNT_B200_PIPELINE=0 ncu --set full --clock-control none --import-source on -k regex:"k_gather|k_wavefront|k_expand" -s 3 -c 3 -f -o $O/general_c4 python tools/one_call.py c4 exact > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/launches_bench_c4.csv python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu-baseline --no-graph --e2e-steps 1 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/launches_bench_c4d.csv python bench.py --workload c4d --steps 2 --warmup 3 --no-cpu-baseline --no-graph --e2e-steps 1 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_gather|k_wavefront|k_expand" -s 3 -c 3 -f -o $O/general_c4 python tools/one_call.py c4 exact > /dev/null 2>&1
 fi
-cat $O/tests.log; cat $O/compact_time.log; for f in $O/bench_c2.json $O/bench_c3.json $O/bench_c4.json $O/bench_c5mb.json; do python -c "
-import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print('$f', d['ms_per_step'], d['roofline']['frac'], (d.get('lse_fast') or {}).get('ms_per_step'), d['e2e']['value'])"; done
+cat $O/tests.log; for f in $O/bench_*.json; do python -c "
+import json,sys
+try:
+    d=json.loads(open('$f').read().strip().splitlines()[-1]); print('$f', round(d['ms_per_step'],4), round(d['roofline']['frac'],3) if 'roofline' in d else None, round(d['e2e']['value']))
+except Exception as e: print('$f', 'FAILED', e)"; done
