@@ -147,10 +147,13 @@ int rnnt_b200_gather_forward(void *stream, void *workspace, size_t workspace_byt
 /* ... and its backward: out (N,T,U,V) = scatter of pair_grads * grad_out[n], zeros elsewhere,
  * every element written (replaces mul_ + GatherBackward's zeros + scatter_add_).
  * accumulate != 0: a label equal to blank adds both gradients (torch scatter_add_, gather=True);
- * accumulate == 0: the label gradient overrides (core.cu launches the label kernel last). */
+ * accumulate == 0: the label gradient overrides (core.cu launches the label kernel last).
+ * yn: with the label lengths a label slot is taken as real iff u < yn[n] (structural); with NULL every u < U-1 is,
+ * and in override mode a label gradient of exactly 0 is read as "no transition" (padded labels may equal blank). */
 int rnnt_b200_gather_backward(void *stream, const float *pair_grads, const int *labels,
                               const float *grad_out, float *out,
-                              int N, int T, int U, int V, int blank, int accumulate);
+                              int N, int T, int U, int V, int blank, int accumulate,
+                              const int *yn /* (N) label lengths, or NULL */);
 
 /* Loss straight from un-normalised logits (the reference needs log-softmaxed input, README.md:59, and its
  * benchmark times F.log_softmax with the loss, pytorch_binding/benchmark.py:65): log_softmax's forward and backward

@@ -54,9 +54,11 @@ def test_native_dense_and_gather(lib, shape):
                                       p(pg), N, T, U, V, 1, ctypes.c_float(0.3), 2)
     assert st == 0
     out = torch.empty_like(xs)
-    st = lib.rnnt_b200_gather_backward(stream, p(pg), p(y), p(scale), p(out), N, T, U, V, 1, 0)
-    assert st == 0
-    np.testing.assert_allclose(out.cpu().numpy(), g0 * scale.cpu().numpy().reshape(-1, 1, 1, 1), atol=2 * tol)
+    for lengths in (None, b):                       # label liveness by value (no lengths) / structural (with yn)
+        out.fill_(7.0)
+        st = lib.rnnt_b200_gather_backward(stream, p(pg), p(y), p(scale), p(out), N, T, U, V, 1, 0, p(lengths))
+        assert st == 0
+        np.testing.assert_allclose(out.cpu().numpy(), g0 * scale.cpu().numpy().reshape(-1, 1, 1, 1), atol=2 * tol)
     # too-small workspace is refused for shapes that need one; invalid arguments are refused
     st = lib.rnnt_b200_loss_dense(stream, p(ws), ctypes.c_size_t(ws.numel()), p(xs), p(y), p(a), p(b), p(costs),
                                   p(grads), None, N, T, U, V, V, ctypes.c_float(0.0), 0)

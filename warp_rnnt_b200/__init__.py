@@ -120,6 +120,7 @@ class RNNTLossGather(torch.autograd.Function):
                                            fastemit_lambda, need, 0)
         ctx.grads = pg if need else None
         ctx.labels = labels
+        ctx.yn = labels_lengths
         ctx.V = log_probs.size(3)
         ctx.blank = blank
         return costs
@@ -129,7 +130,7 @@ class RNNTLossGather(torch.autograd.Function):
         if ctx.grads is None:
             return None, None, None, None, None, None
         go = grads_output.contiguous().to(ctx.grads.dtype)
-        g = _C.rnnt_gather_backward(ctx.grads, ctx.labels, go, ctx.V, ctx.blank, True)
+        g = _C.rnnt_gather_backward(ctx.grads, ctx.labels, go, ctx.V, ctx.blank, True, ctx.yn)
         return g, None, None, None, None, None
 
 

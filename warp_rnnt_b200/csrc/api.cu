@@ -429,11 +429,11 @@ int rnnt_b200_logits_backward(void *stream, const float *logits, const float *ls
 }
 
 int rnnt_b200_gather_backward(void *stream, const float *pair_grads, const int *labels, const float *grad_out,
-                              float *out, int N, int T, int U, int V, int blank, int accumulate) {
+                              float *out, int N, int T, int U, int V, int blank, int accumulate, const int *yn) {
     if (!dense_args_ok(N, T, U, V) || blank < 0 || blank >= V) return RNNT_STATUS_INVALID_ARGUMENT;
     if (reinterpret_cast<uintptr_t>(pair_grads) & 7u) return RNNT_STATUS_INVALID_ARGUMENT;
     if (N == 0) return RNNT_STATUS_SUCCESS;
-    Problem p = {nullptr, nullptr, nullptr, nullptr, N, T, U, 0};
+    Problem p = {nullptr, yn, nullptr, nullptr, N, T, U, 0};     // yn (optional): which labels are real
     ExpandSrc src = {};
     src.pg = reinterpret_cast<const float2 *>(pair_grads);
     src.scale = grad_out;

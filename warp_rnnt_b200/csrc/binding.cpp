@@ -385,7 +385,7 @@ std::tuple<at::Tensor, at::Tensor> rnnt_joint_pack_backward(const at::Tensor &dx
 }
 
 at::Tensor rnnt_gather_backward(const at::Tensor &pair_grads, const at::Tensor &ys, const at::Tensor &grad_out,
-                                int64_t V, int blank, bool accumulate) {
+                                int64_t V, int blank, bool accumulate, const c10::optional<at::Tensor> &yn) {
     TORCH_CHECK(pair_grads.is_contiguous() && pair_grads.scalar_type() == at::ScalarType::Float &&
                     pair_grads.device().is_cuda() && pair_grads.dim() == 4 && pair_grads.size(3) == 2,
                 "pair_grads must be a contiguous CUDA Float tensor of shape (N, T, U, 2)");
@@ -397,11 +397,18 @@ at::Tensor rnnt_gather_backward(const at::Tensor &pair_grads, const at::Tensor &
     const int64_t N = pair_grads.size(0), T = pair_grads.size(1), U = pair_grads.size(2);
     TORCH_CHECK(ys.dim() == 2 && ys.size(0) == N && ys.size(1) + 1 == U, "ys shape (N, U-1) mismatched");
     TORCH_CHECK(blank >= 0 && blank < V, "blank must be in [0, V)");
+    const int *ynp = nullptr;
+    if (yn.has_value() && yn->defined()) {
+        TORCH_CHECK(yn->is_contiguous() && yn->scalar_type() == at::ScalarType::Int && yn->device() == pair_grads.device() &&
+                        yn->numel() == N,
+                    "yn must be a contiguous Int tensor of shape (N,) on the device of pair_grads");
+        ynp = yn->data_ptr<int>();
+    }
     const c10::cuda::CUDAGuard guard(pair_grads.device());
     at::Tensor out = at::empty({N, T, U, V}, pair_grads.options());
     check_status(rnnt_b200_gather_backward(current_stream(pair_grads), pair_grads.data_ptr<float>(),
                                            ys.data_ptr<int>(), grad_out.data_ptr<float>(), out.data_ptr<float>(),
-                                           (int)N, (int)T, (int)U, (int)V, blank, accumulate ? 1 : 0));
+                                           (int)N, (int)T, (int)U, (int)V, blank, accumulate ? 1 : 0, ynp));
     return out;
 }
 
@@ -435,7 +442,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("blank") = 0, py::arg("fastemit_lambda") = 0.0, py::arg("want_grads") = true,
           py::arg("lse_mode") = 0);
     m.def("rnnt_gather_backward", &rnnt_gather_backward, py::arg("pair_grads"), py::arg("ys"), py::arg("grad_out"),
-          py::arg("V"), py::arg("blank") = 0, py::arg("accumulate") = false);
+          py::arg("V"), py::arg("blank") = 0, py::arg("accumulate") = false, py::arg("yn") = py::none());
     m.def("set_lse_mode", [](int mode) { rnnt_b200_set_lse_mode(mode); }, py::arg("mode"));
     m.def("get_lse_mode", []() { return rnnt_b200_get_lse_mode(); });
     m.def("launch_count", []() { return rnnt_b200_launch_count(); });

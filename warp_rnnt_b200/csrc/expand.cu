@@ -70,7 +70,9 @@ __device__ __forceinline__ void stage_row(const Problem &p, const ExpandSrc &src
             const float sc = src.scale ? src.scale[n] : 1.0f;
             const float2 q = src.pg[c];
             g = make_float2(q.x * sc, q.y * sc);
-            if ((int)u < p.U - 1) lab = src.labels[(int64_t)n * (p.U - 1) + u];
+            // label transition out of (t,u) exists iff u < yn[n]; without lengths (p.yn == null) every u < U-1 is taken
+            // and the sweep falls back to "a zero label gradient means none" in override mode
+            if ((int)u < (p.yn ? min(p.yn[n], p.U - 1) : p.U - 1)) lab = src.labels[(int64_t)n * (p.U - 1) + u];
         } else {
             const Lattice L = get_lattice(p, (int)n);
             const bool live = L.ok && !(src.bad && src.bad[n]);
@@ -130,7 +132,7 @@ k_expand(Problem p, ExpandSrc src, OUT *__restrict__ out, int64_t cells, int V, 
             const int lab = s_lab[row];
             float x = (v == blank) ? g.x : 0.0f;
             // override mode: a zero label gradient marks "no label transition here" (padded labels may equal blank)
-            if (v == lab) x = (MODE == 1 && src.label_adds) ? x + g.y : ((MODE == 1 && g.y == 0.0f) ? x : g.y);
+            if (v == lab) x = (MODE == 1 && src.label_adds) ? x + g.y : ((MODE == 1 && !p.yn && g.y == 0.0f) ? x : g.y);
             return x;
         };
         int64_t a0 = vec_ok ? min(f1, (f0 + VEC - 1) & ~(int64_t)(VEC - 1)) : f1;
@@ -161,7 +163,7 @@ k_expand(Problem p, ExpandSrc src, OUT *__restrict__ out, int64_t cells, int V, 
                 const int lab = s_lab[row];
                 const int pb = blank - v, pl = lab - v;
                 const bool adds = (MODE == 1) && src.label_adds;
-                const bool lab_live = (MODE != 1) || adds || (g.y != 0.0f);
+                const bool lab_live = (MODE != 1) || adds || p.yn || (g.y != 0.0f);
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
                     float x = (k == pb) ? g.x : 0.0f;
