@@ -57,6 +57,8 @@ WORKLOADS = {
               "N=64 T=600 U=150 V=1024 bfloat16 i/o = a double-size micro-batch of BASELINE configs[4]"),
     "c2l": (128, 150, 40, 28, "logits", False,
             "N=128 T=150 U=40 V=28 from un-normalised logits (log_softmax fused; gradient w.r.t. logits)"),
+    "c5mbl": (32, 600, 150, 1024, "logits", False,
+              "N=32 T=600 U=150 V=1024 from un-normalised logits = one micro-batch of BASELINE configs[4], log_softmax fused"),
 }
 API_CALL = {"dense": "warp_rnnt_b200.rnnt_loss(x, ..., reduction='sum').backward()",
             "gather": "warp_rnnt_b200.rnnt_loss(x, ..., reduction='sum', gather=True).backward()",
@@ -362,6 +364,16 @@ def main():
             for i in range(3):
                 api_step(sets[i % R])
             extra["api_eager_ms_per_step"] = timed(lambda i: api_step(sets[i % R]), min(args.steps, 30), 1, dist, dev) / min(args.steps, 30)
+        if mode == "logits":
+            # the same result the reference's way: torch.log_softmax, then the loss, autograd through both
+            def unfused(i):
+                x = sets[i % R][0]
+                x.grad = None
+                w.rnnt_loss(torch.log_softmax(x, -1), *sets[i % R][1:], reduction="sum").backward()
+            for i in range(3):
+                unfused(i)
+            extra["unfused_ms_per_step"] = timed(unfused, min(args.steps, 20), 1, dist, dev) / min(args.steps, 20)
+            extra["unfused_call"] = "warp_rnnt_b200.rnnt_loss(torch.log_softmax(logits, -1), ..., reduction='sum').backward(), eager"
         if mode == "dense":
             keep = [None] * R
 

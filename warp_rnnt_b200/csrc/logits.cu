@@ -38,7 +38,18 @@ k_lse_pairs(const float *__restrict__ x, const int *__restrict__ labels, int64_t
             if (a > m) { s = s * expf(m - a); m = a; }        // (m == -inf: s is 0, exp(-inf) = 0)
             s += expf(a - m);
         };
-        if (VEC4) {
+        if (VEC4 && (V >> 2) <= SUB) {
+            // the whole row is one float4 per lane: max first (shuffles only), then ONE exp per element -- the online
+            // merge below would spend two more exp per lane and shuffle round
+            const bool has = sub < (V >> 2);
+            const float4 a = has ? __ldg(reinterpret_cast<const float4 *>(row) + sub) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            m = fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w));
+#pragma unroll
+            for (int o = SUB / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            s = has ? (expf(a.x - m) + expf(a.y - m)) + (expf(a.z - m) + expf(a.w - m)) : 0.0f;
+#pragma unroll
+            for (int o = SUB / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        } else if (VEC4) {
             const float4 *row4 = reinterpret_cast<const float4 *>(row);
             for (int q = sub; q < (V >> 2); q += SUB) {
                 const float4 a = __ldg(row4 + q);
@@ -54,7 +65,7 @@ k_lse_pairs(const float *__restrict__ x, const int *__restrict__ labels, int64_t
         } else {
             for (int v = sub; v < V; v += SUB) add(__ldg(row + v));
         }
-        if (SUB > 1) {
+        if (SUB > 1 && !(VEC4 && (V >> 2) <= SUB)) {
 #pragma unroll
             for (int o = SUB / 2; o > 0; o >>= 1) {
                 const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
