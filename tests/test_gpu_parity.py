@@ -413,3 +413,51 @@ def test_reference_binding_on_our_c_abi_all_layouts(w, compat, ref):
     bm = compat.rnnt_loss_compact_backward(go, gm, cumlen, lm, V, blank)
     assert torch.equal(bm, br)
     w.set_lse_mode("auto")
+
+
+# ------------------------------------------------------------------ the emit's row-pair path (V % 4 == 2)
+@pytest.mark.parametrize("V", [6, 10, 50])
+def test_expand_row_pair_path_all_modes(w, ref, V):
+    """k_expand sweeps two rows at a time when V % 4 == 2 (float output): dense forward (label overrides blank), python
+    gather=True backward (label adds to blank), compact backward -- on a lattice too large for the fused kernel, with
+    odd and even row counts per chunk, labels that equal the blank, and an output base that is only 16-byte aligned."""
+    N, T, U = 3, 301, 47
+    lp, ys, xn, yn = make_inputs(N, T, U, V, seed=V, random_lengths=True, blank=1)
+    ys[0, :5] = 1                                                    # labels equal to blank = 1
+    args = (cu(ys), cu(xn), cu(yn))
+    w.set_lse_mode("exact")
+    try:
+        c0, g0 = oracle.dense(lp, ys, xn, yn, blank=1, fastemit_lambda=0.1)
+        costs, grads = w._C.rnnt_loss(cu(lp), *args, blank=1, fastemit_lambda=0.1)
+        np.testing.assert_allclose(costs.cpu().numpy(), c0, rtol=1e-5)
+        assert np.abs(grads.cpu().numpy() - g0).max() <= gtol(T, U)
+        if ref is not None:
+            cr, gr = ref.rnnt_loss(cu(lp), *args, blank=1, fastemit_lambda=0.1)
+            assert torch.equal(costs, cr) and torch.equal(grads, gr)
+        # gather=True: torch.gather's backward adds the label gradient to the blank one where they coincide
+        x = cu(lp).requires_grad_(True)
+        go = cu(np.linspace(0.5, 1.5, N).astype(np.float32))
+        (w.rnnt_loss(x, *args, blank=1, gather=True, fastemit_lambda=0.1) * go).sum().backward()
+        g = gather_np(lp, ys, 1)
+        _, gp = oracle.dense(g, ys, xn, yn, blank=-1, fastemit_lambda=0.1)
+        expect = np.zeros_like(lp, dtype=np.float64)
+        n_i, t_i, u_i = np.meshgrid(np.arange(N), np.arange(T), np.arange(U - 1), indexing="ij")
+        np.add.at(expect, (n_i, t_i, u_i, ys[n_i, u_i]), gp[:, :, :U - 1, 1])
+        expect[..., 1] += gp[..., 0]
+        expect *= go.cpu().numpy().reshape(-1, 1, 1, 1)
+        assert np.abs(x.grad.cpu().numpy() - expect).max() <= 2 * gtol(T, U)
+        # compact backward
+        xs_c, ys_c = to_compact(lp, ys, xn, yn)
+        cargs = (cu(xs_c), cu(ys_c), cu(xn), cu(yn))
+        cm, gm, lm = w._C.rnnt_loss_compact(*cargs, blank=1, fastemit_lambda=0.1)
+        cumlen = torch.cumsum(cu(xn) * (cu(yn) + 1), dim=0, dtype=torch.int32)
+        bm = w._C.rnnt_loss_compact_backward(go, gm, cumlen, lm, V, 1)
+        c1, pg1, loc1 = oracle.compact(xs_c, ys_c, xn, yn, blank=1, fastemit_lambda=0.1)
+        b1 = oracle.compact_scatter(go.cpu().numpy(), pg1, loc1, cumlen.cpu().numpy(), V, 1)
+        assert np.abs(bm.cpu().numpy() - b1).max() <= 2 * gtol(T, U)
+        if ref is not None:
+            cr, gr, lr = ref.rnnt_loss_compact(*cargs, blank=1, fastemit_lambda=0.1)
+            br = ref.rnnt_loss_compact_backward(go, gm, cumlen, lm, V, 1)
+            assert torch.equal(bm, br)
+    finally:
+        w.set_lse_mode("auto")

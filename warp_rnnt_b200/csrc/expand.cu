@@ -106,10 +106,16 @@ __device__ __forceinline__ void st_one(__nv_bfloat16 *p, float v) { *p = __float
 template <int MODE, typename OUT = float>
 __global__ void __launch_bounds__(kExpandThreads)
 k_expand(Problem p, ExpandSrc src, OUT *__restrict__ out, int64_t cells, int V, int blank, int rows_per_chunk,
-         FastDiv divV, FastDiv divU, FastDiv divTU, int vec_ok) {
+         FastDiv divV, FastDiv divU, FastDiv divTU, int vec_ok, FastDiv divG) {
     constexpr int VEC = 16 / (int)sizeof(OUT);          // output elements per 16-byte vector
     __shared__ float2 s_g[kExpandMaxRows];
     __shared__ int s_lab[kExpandMaxRows];
+    // V % 4 == 2 (float output): two consecutive rows are V/2 whole vectors.  Per row (blank grad, label grad, label
+    // position or a far-away "none"), with the label-equals-blank rules already applied, so that the sweep of a
+    // row pair is four compare/selects per float and nothing else (see below).
+    __shared__ __align__(16) float4 s_q[(VEC == 4) ? kExpandMaxRows + 2 : 1];
+    constexpr int kNoLabel = -(1 << 24);
+    const bool pair_path = (VEC == 4) && ((V & 3) == 2) && vec_ok && ((rows_per_chunk & 1) == 0);
     const int64_t nchunks = (cells + rows_per_chunk - 1) / rows_per_chunk;
     for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         const int64_t r0 = chunk * rows_per_chunk;
@@ -122,7 +128,16 @@ k_expand(Problem p, ExpandSrc src, OUT *__restrict__ out, int64_t cells, int V, 
             stage_row<MODE>(p, src, r0 + r, blank, divU, divTU, g, lab);
             s_g[r] = g;
             s_lab[r] = lab;
+            if (VEC == 4 && pair_path) {
+                const bool adds = (MODE == 1) && src.label_adds;
+                float gb = g.x;
+                int le = lab;
+                if (lab < 0 || (MODE == 1 && !adds && !p.yn && g.y == 0.0f)) le = kNoLabel;    // no label transition here
+                else if (adds && lab == blank) { gb += g.y; le = kNoLabel; }                   // scatter_add semantics
+                s_q[r] = make_float4(gb, g.y, __int_as_float(le), 0.0f);
+            }
         }
+        if (VEC == 4 && pair_path && threadIdx.x < 2) s_q[rows + threadIdx.x] = make_float4(0.0f, 0.0f, __int_as_float(kNoLabel), 0.0f);
         __syncthreads();
         // ---- phase 2: sweep the chunk's floats [f0, f1)
         const int64_t f0 = r0 * (int64_t)V;
@@ -148,6 +163,29 @@ k_expand(Problem p, ExpandSrc src, OUT *__restrict__ out, int64_t cells, int V, 
             const uint32_t row = divV.div(local);
             st_one(out + f, value((int)row, (int)(local - row * V)));
         }
+        if (VEC == 4 && pair_path) {
+            // rows come in pairs of G = V/2 vectors (r0 is even, so a0 == f0): vector k of pair q covers positions
+            // [4k, 4k+4) of the pair's 2V floats; the four candidate non-zeros sit at blank, label(row0), V + blank,
+            // V + label(row1).  The label is applied after its row's blank (it overrides, core.cu:383-390).
+            const uint32_t nvec = (uint32_t)((a1 - a0) >> 2), G = (uint32_t)V >> 1;
+            float *o4 = reinterpret_cast<float *>(out) + a0;
+            for (uint32_t i = threadIdx.x; i < nvec; i += kExpandThreads) {
+                const uint32_t q = divG.div(i);
+                const int p0 = (int)(4u * (i - q * G));
+                const float4 A = s_q[2 * q], B = s_q[2 * q + 1];
+                const int ab = blank - p0, al = __float_as_int(A.z) - p0, bb = ab + V, bl = __float_as_int(B.z) - p0 + V;
+                float e[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float x = (ab == k) ? A.x : 0.0f;
+                    x = (al == k) ? A.y : x;
+                    x = (bb == k) ? B.x : x;
+                    x = (bl == k) ? B.y : x;
+                    e[k] = x;
+                }
+                st_cs_v4(o4 + 4 * (size_t)i, make_float4(e[0], e[1], e[2], e[3]));
+            }
+        } else
         for (int64_t f = a0 + VEC * (int64_t)threadIdx.x; f < a1; f += VEC * kExpandThreads) {
             const uint32_t local = (uint32_t)(f - f0);
             uint32_t row = divV.div(local);
@@ -259,6 +297,7 @@ cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src
     if (cells <= 0) return cudaSuccess;
     int rows = (int)(65536 / ((int64_t)V * (io_bf16 ? 2 : 4)));
     rows = max(1, min(rows, kExpandMaxRows));
+    if (rows > 1) rows &= ~1;                          // whole row pairs per chunk (the V % 4 == 2 path pairs rows)
     const int64_t nchunks = (cells + rows - 1) / rows;
     const int sms = sm_count(current_device());
     // persistent CTAs by default; retire_early = one CTA per few chunks, so that SM resources keep freeing
@@ -266,18 +305,19 @@ cudaError_t launch_expand(cudaStream_t s, const Problem &p, const ExpandSrc &src
     const int64_t cap = retire_early ? (int64_t)sms * 64 : (int64_t)sms * 8;
     const int grid = (int)(nchunks < cap ? nchunks : cap);
     const FastDiv divV((uint32_t)V), divU((uint32_t)max(p.U, 1)), divTU((uint32_t)max(p.T * p.U, 1));
+    const FastDiv divG((uint32_t)max(V / 2, 1));      // vectors per row pair when V % 4 == 2
     const int vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) ? 1 : 0;
     const int mode = p.compact ? 2 : (src.pg ? 1 : 0);
     if (io_bf16) {
         if (mode != 0) return cudaErrorInvalidValue;    // bf16 output: the dense forward emit only
         k_expand<0, __nv_bfloat16><<<grid, kExpandThreads, 0, s>>>(p, src, static_cast<__nv_bfloat16 *>(out_v), cells, V, blank, rows, divV,
-                                                               divU, divTU, vec_ok);
+                                                               divU, divTU, vec_ok, divG);
         count_launch();
         return cudaGetLastError();
     }
-    if (mode == 0) k_expand<0><<<grid, kExpandThreads, 0, s>>>(p, src, out, cells, V, blank, rows, divV, divU, divTU, vec_ok);
-    else if (mode == 1) k_expand<1><<<grid, kExpandThreads, 0, s>>>(p, src, out, cells, V, blank, rows, divV, divU, divTU, vec_ok);
-    else k_expand<2><<<grid, kExpandThreads, 0, s>>>(p, src, out, cells, V, blank, rows, divV, divU, divTU, vec_ok);
+    if (mode == 0) k_expand<0><<<grid, kExpandThreads, 0, s>>>(p, src, out, cells, V, blank, rows, divV, divU, divTU, vec_ok, divG);
+    else if (mode == 1) k_expand<1><<<grid, kExpandThreads, 0, s>>>(p, src, out, cells, V, blank, rows, divV, divU, divTU, vec_ok, divG);
+    else k_expand<2><<<grid, kExpandThreads, 0, s>>>(p, src, out, cells, V, blank, rows, divV, divU, divTU, vec_ok, divG);
     count_launch();
     return cudaGetLastError();
 }
