@@ -151,6 +151,24 @@ k_gather(Problem p, const IO *__restrict__ lp, const int *__restrict__ labels, i
 
 struct __align__(8) Slot { float val; int row; };
 
+// shared-space (32-bit) addresses, computed once per sweep: a generic pointer costs an address-space conversion
+// (S2UR + ULEA in a cluster launch) at every access, ~10 of the loop's instructions per step
+__device__ __forceinline__ Slot ld_slot_s(uint32_t a) {
+    Slot s;
+    asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];" : "=f"(s.val), "=r"(s.row) : "r"(a) : "memory");
+    return s;
+}
+__device__ __forceinline__ void st_slot_s(uint32_t a, float v, int row) {
+    asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "f"(v), "r"(row) : "memory");
+}
+__device__ __forceinline__ int ld_vol_s32_s(uint32_t a) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_vol_s32_s(uint32_t a, int v) {
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ Slot ld_slot(const Slot *p) {
     Slot s;
     asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];"
@@ -250,11 +268,13 @@ __device__ __forceinline__ float sweep_warp(const Sweep &S) {
 
     // operands of step s into prefetch slot k.  Predicated loads that write the destination
     // register directly (a select after the load would make the prefetch wait for its own data).
+    // fetch() is called for s = 0, 1, 2, ... in order: the cell pointers run along (two 64-bit adds per step instead of
+    // a 64-bit multiply-add and the pointer arithmetic per load)
+    const float *cell = reinterpret_cast<const float *>(S.pr + c0);
+    const float *bcell = S.o + c0 + bcol;
     auto fetch = [&](int k, int s) {
         const int i = s - lane;
         const bool in = (unsigned)i < rows;
-        const int64_t c = c0 + (int64_t)s * ds;
-        const float *cell = reinterpret_cast<const float *>(S.pr + c);
         if (BETA) {
             wb[k] = ldg_nc_pred(cell, in, 0.0f);
             wl[k] = ldg_nc_pred(cell + 1, in && !first_col, (i < 0 || first_col) ? kBig : 0.0f);
@@ -262,25 +282,31 @@ __device__ __forceinline__ float sweep_warp(const Sweep &S) {
             wb[k] = ldg_nc_pred(cell - 2 * (int64_t)st, in && i >= 1, 0.0f);
             wl[k] = ldg_nc_pred(cell - 1, in && !first_col, (i < 0 || first_col) ? kBig : 0.0f);
         }
-        if (SRC == kLeftMem) bnd[k] = ldg_cg_pred(S.o + c + bcol, in && mem_lane && (!S.override0 || i >= 1), kBig);
+        if (SRC == kLeftMem) {
+            bnd[k] = ldg_cg_pred(bcell, in && mem_lane && (!S.override0 || i >= 1), kBig);
+            bcell += ds;
+        }
+        cell += 2 * ds;
     };
 
+    const uint32_t a_in = (uint32_t)__cvta_generic_to_shared(S.ring_in), a_out = (uint32_t)__cvta_generic_to_shared(S.ring_out);
+    const uint32_t a_cself = (uint32_t)__cvta_generic_to_shared(S.cons_self), a_cnext = (uint32_t)__cvta_generic_to_shared(S.cons_next);
     // consumer side of the ring: value of the left neighbour column at row `row` (warp-uniform call)
     auto ring_get = [&](int row) -> float {
-        while (pre.row != row) pre = ld_slot(&S.ring_in[row & S.ring_mask]);
+        while (pre.row != row) pre = ld_slot_s(a_in + 8u * (uint32_t)(row & S.ring_mask));
         const float v = pre.val;
-        if (S.backpressure && lane == 0) st_vol_s32(S.cons_self, row + 1);
-        pre = ld_slot(&S.ring_in[(row + 1) & S.ring_mask]);   // next row, off the dependent chain
+        if (S.backpressure && lane == 0) st_vol_s32_s(a_cself, row + 1);
+        pre = ld_slot_s(a_in + 8u * (uint32_t)((row + 1) & S.ring_mask));   // next row, off the dependent chain
         return v;
     };
     // producer side: lane 31 hands row `row` of its column to the next warp (warp-uniform call)
     auto ring_put = [&](int row, float v) {
         if (S.backpressure && row - S.ring_mask - 1 >= cons_seen) {
-            int c = ld_vol_s32(S.cons_next);
-            while (row - S.ring_mask - 1 >= c) c = ld_vol_s32(S.cons_next);
+            int c = ld_vol_s32_s(a_cnext);
+            while (row - S.ring_mask - 1 >= c) c = ld_vol_s32_s(a_cnext);
             cons_seen = c;
         }
-        if (lane == 31) st_slot(&S.ring_out[row & S.ring_mask], v, row);
+        if (lane == 31) st_slot_s(a_out + 8u * (uint32_t)(row & S.ring_mask), v, row);
     };
 
 #pragma unroll
