@@ -91,7 +91,10 @@ size_t rnnt_b200_workspace_bytes(int64_t cells, int N);
  *   log_probs (N,T,U,V) f32 log-softmaxed; labels (N,U-1) i32; xn,yn (N) i32
  *   costs (N) f32 out;  grads (N,T,U,V) f32 out, every element written (NULL = forward only)
  *   grad_scale (N) f32 or NULL: grads[n] *= grad_scale[n]
- *   blank in [0,V).  fastemit_lambda scales label gradients only (core.cu:327-329). */
+ *   blank in [0,V).  fastemit_lambda scales label gradients only (core.cu:327-329).
+ * Lengths are NOT validated on the host (that would need a device->host copy): a sample with xn outside [1,T] or
+ * yn+1 outside [1,U] gets cost NaN and an all-zero gradient slab, the call still returns RNNT_STATUS_SUCCESS (the
+ * reference reads out of bounds in that case).  Callers that cannot trust their lengths check costs for NaN. */
 int rnnt_b200_loss_dense(void *stream, void *workspace, size_t workspace_bytes,
                          const float *log_probs, const int *labels, const int *xn, const int *yn,
                          float *costs, float *grads, const float *grad_scale,

@@ -282,7 +282,7 @@ cudaError_t launch_rescale(cudaStream_t s, void *grads, const float *grad_out, i
     if (N <= 0 || elems_per_sample <= 0) return cudaSuccess;
     const int sms = sm_count(current_device());
     int64_t gx = (elems_per_sample / 4 + kRescaleThreads * 8 - 1) / (kRescaleThreads * 8);
-    const int64_t cap = ((int64_t)sms * 8 + N - 1) / N;
+    const int64_t cap = ((int64_t)sms * 2 + N - 1) / N;      // few CTAs: in the usual case every one of them returns at once
     gx = max((int64_t)1, min(gx, cap));
     dim3 grid((unsigned)gx, (unsigned)N);
     if (io_bf16) k_rescale_bf16<<<grid, kRescaleThreads, 0, s>>>(static_cast<__nv_bfloat16 *>(grads), grad_out, grad_out_stride, applied, elems_per_sample);
