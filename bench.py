@@ -459,6 +459,20 @@ def main():
                "compact": "k_prefix + k_gather + k_wavefront + k_grads_pairs + k_expand<2>",
                "bf16": "k_fused<exact,dense,bf16>" if args.workload == "c2b" else "k_gather<bf16> + k_wavefront + k_expand<0,bf16>",
                "logits": "k_lse_pairs + k_fused<exact,pairs> + k_expand_logits"}[mode]
+    # dram__bytes_read + dram__bytes_write of the dominant kernel: from the committed ncu --set full capture of the same
+    # workload (profiles/), labelled as such -- it is NOT measured in this run
+    traffic, traffic_note = None, "not measured in this run; ncu dram__bytes per launch are in profiles/"
+    key = {"c2": "c2", "c4d": "c4"}.get(args.workload)
+    summ = os.path.join(ROOT, "profiles", "r2_summary.json")
+    if key and world == 1 and os.path.exists(summ):
+        try:
+            ent = json.load(open(summ)).get(key)
+            if ent:
+                traffic = ent["dram_bytes_per_launch"]
+                traffic_note = ("from the committed ncu --set full capture of this workload (profiles/r2_summary.json, kernel %s), "
+                                "not measured in this run" % ent.get("kernel", "?")[:60])
+        except Exception:
+            pass
     out = {
         "metric": "RNN-T loss+grad lattices/sec", "value": value, "unit": "lattices/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -468,7 +482,7 @@ def main():
         "timed_call": API_CALL[mode] + " -- " + graph_note,
         "lse_mode": args.lse + (" (= exact: results bit-identical to the reference kernels)" if args.lse == "auto" else ""),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "traffic_note": "not measured in this run; ncu dram__bytes per launch are in profiles/",
+                     "traffic": traffic, "traffic_source": traffic_note,
                      "algorithmic_bytes_per_launch": balg, "peak_source": peak_src, "kernel": kernels,
                      "kernel_ms": kernel_ms,
                      "kernel_ms_source": ("CUDA events over back-to-back operator calls (_C.rnnt_loss = the one kernel)"

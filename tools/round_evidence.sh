@@ -16,7 +16,7 @@ echo "== synccheck";                                timeout 300 compute-sanitize
 } > $O/tests.log 2>&1
 python bench.py --steps 100 --warmup 10 > $O/bench_c2.json 2> $O/bench_c2.err
 if [ "${REF:-0}" = 1 ]; then python bench.py --impl reference --steps 5 --warmup 3 > $O/bench_c2_reference.json 2> $O/bench_c2_reference.err; fi
-for w in c2g c3 c3d c4 c4d c5mb c2b c5mbb c2l; do timeout 400 python bench.py --workload $w --steps 20 --warmup 5 > $O/bench_$w.json 2> $O/bench_$w.err; done
+for w in c2g c3 c3d c4 c4d c5mb c2b c5mbb c2l c5mbl; do timeout 400 python bench.py --workload $w --steps 20 --warmup 5 > $O/bench_$w.json 2> $O/bench_$w.err; done
 python tools/fused_timeline.py c2 $O/timeline_c2.json > $O/timeline_c2.log 2>&1
 python tools/fused_timeline.py c3 $O/timeline_c3.json > $O/timeline_c3.log 2>&1
 # launch lists: the API step as the bench runs it (eager, so that ncu sees every launch), cold-cache + serialised: shares only
