@@ -2,29 +2,31 @@
 // ((T+U)*U <~ 9k cells: BASELINE configs 1-3).  One launch does everything the reference spreads
 // over zeros_like + 4 kernels (+ python gather / mul_):
 //
-//   phase 0  gather      up to 14 warps stage the lattice's blank/label log-probs into shared memory in
-//                        DIAGONAL-MAJOR, target-indexed form (replaces the python-level gather,
-//                        __init__.py:118-128, and the strided loads inside kernel_warp, core.cu:115-120):
-//                        one TMA bulk copy per lattice row (U*V contiguous floats) into the warp's row
-//                        buffer, then two LDS per cell pick blank and label (fallback: LDG picks in
-//                        128-cell chunks).  Rows are staged from both ends towards the middle and each
-//                        warp publishes its progress (st.release), so the two wavefronts START WHILE THE
-//                        GATHER IS STILL RUNNING and chase it (alpha needs the top rows first, beta the
-//                        bottom rows)
-//   phase 1  wavefront   ONE warp runs alpha and one runs beta: lane l owns C adjacent lattice columns,
-//                        every anti-diagonal is one step = one shuffle + C independent LSE chains,
-//                        operands and results move as C-wide vector LDS/STS (conflict-free, because a
-//                        diagonal's cells are contiguous in the staged layout).  No inter-warp hand-off,
-//                        no barrier, no atomics on the recurrence (replaces kernel_warp + the
-//                        global-memory counts scheduler, core.cu:41-258)
-//            zero-fill   when the gather is done, the gather warps' lane 0 issue TMA bulk stores of a
-//                        zeroed shared-memory buffer (evict_last) over this CTA's slice of the dense
-//                        gradient (replaces at::zeros_like, binding.cpp:58); fallback: 256-bit stores
-//   phase 2  cost/guard  kernel_fill_costs (core.cu:334-370)
-//            patch       the <= 2 non-zeros per row are written into the freshly zeroed, still L2-resident
-//                        lines (kernel_grads_blank/label, core.cu:260-332), or -- MODE 1 -- the gradients
-//                        are emitted in (N,T,U,2) form for the deferred dense backward (+ loc for the
-//                        compact layout, whose lattices are addressed through mem_pref / lab_pref).
+//   phase 0  gather      gather warps stage the lattice's blank/label log-probs into shared memory ONCE, in
+//                        diagonal-major form indexed the beta way (replaces the python-level gather,
+//                        __init__.py:118-128, and the strided loads inside kernel_warp, core.cu:115-120): one TMA
+//                        bulk copy per lattice row (U*V contiguous elements, f32 or bf16) into a row buffer -- two
+//                        buffers per gather warp, so the next row is in flight while this one is picked apart -- then
+//                        two LDS per cell pick blank and label (fallback: LDG picks in 128-cell chunks).  Rows are
+//                        staged from both ends towards the middle and each warp publishes its progress (st.release),
+//                        so the two wavefronts START WHILE THE GATHER IS STILL RUNNING and chase it (alpha needs the
+//                        top rows first, beta the bottom rows)
+//   phase 1  wavefront   ONE warp runs alpha and one runs beta: lane l owns C adjacent lattice columns, every
+//                        anti-diagonal is one step = one shuffle + C independent LSE chains, operands and results
+//                        move as C-wide vector LDS/STS (a diagonal's cells are contiguous in the staged layout; alpha
+//                        walks the same planes as beta, backwards).  No inter-warp hand-off, no barrier, no atomics on
+//                        the recurrence (replaces kernel_warp + the global-memory counts scheduler, core.cu:41-258)
+//            zero-fill   when the gather is done, two warps' lane 0 issue TMA bulk stores of a zeroed shared-memory
+//                        buffer (evict_last) over this CTA's slice of the dense gradient (replaces at::zeros_like,
+//                        binding.cpp:58); fallback: 256-bit stores
+//            chase       the other free warps follow the two wavefronts from the middle anti-diagonal outwards and
+//                        replace each staged log-prob by (alpha + beta) + log-prob: all of the gradient that does not
+//                        need beta[0,0]
+//   phase 2  cost/guard  kernel_fill_costs (core.cu:334-370) + the reduced loss sum_n costs[n]*scale[n] by the last CTA
+//            patch       expf(x - beta00) and <= 2 four-byte stores per cell into the freshly zeroed, still L2-resident
+//                        lines (kernel_grads_blank/label, core.cu:260-332), or -- MODE 1 -- the gradients are emitted
+//                        in (N,T,U,2) form for the deferred dense backward (+ loc for the compact layout, whose
+//                        lattices are addressed through mem_pref / lab_pref).
 //
 // grid (S, N): S CTAs per lattice recompute the (cheap) wavefront redundantly and split the
 // (bandwidth-bound) fill/patch of the lattice's rows, so small batches still use every SM.
