@@ -46,7 +46,8 @@ def test_bench_line_has_contract_keys(name):
 
 R2 = ["r2_bench_ours.json", "r2_bench_c2g.json", "r2_bench_c3.json", "r2_bench_c3d.json", "r2_bench_c4.json",
       "r2_bench_c4d.json", "r2_bench_c5mb.json", "r2_bench_c2b.json", "r2_bench_c5mbb.json", "r2_bench_c2l.json",
-      "r2_bench_c5mbl.json", "r2_bench_c2_2gpu_builder.json", "r2_bench_c2_4gpu_builder.json"]
+      "r2_bench_c5mbl.json", "r2_bench_c2_2gpu_builder.json", "r2_bench_c2_4gpu_builder.json",
+      "r2_bench_c2_8gpu_builder.json"]
 
 
 @pytest.mark.parametrize("name", R2)
