@@ -78,6 +78,12 @@ void rnnt_b200_debug_fused_trace(void *buf);
  * Process-wide; affects the dense and gathered layouts (the compact reference has no guard). */
 void rnnt_b200_debug_guard_poison(int n, float delta);
 
+/* Diagnostics (tests only): the exact LSE's log1p is libdevice's main path restated without its unreachable tail
+ * (csrc/common.cuh).  This kernel compares it with libdevice's log1pf on EVERY float in [+0, 1] (the range of
+ * expf(d <= 0)), on NaN, and the complete exact LSE flavours on pseudo-random operand pairs; it ADDS the number of
+ * bit mismatches to *mismatches (device memory, zeroed by the caller).  Must stay 0. */
+int rnnt_b200_debug_lse_selfcheck(void *stream, unsigned long long *mismatches);
+
 /* ------------------------------------------------------------------------------------------
  * (A) native interface
  * ------------------------------------------------------------------------------------------ */

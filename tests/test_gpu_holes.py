@@ -296,3 +296,13 @@ def test_two_devices_in_one_process(w):
             assert np.abs(outs[1][1][:k].numpy() - g0).max() <= gtol(T, U), what
     finally:
         w.set_lse_mode("auto")
+
+
+def test_exact_log1p_restatement_is_libdevice_bit_for_bit(lib):
+    """The exact LSE's log1p is libdevice's main path without its unreachable tail (csrc/common.cuh:log1pf_unit).
+    The library's self-check kernel compares it with log1pf on EVERY float in [+0, 1] (2^30 - 2^23 + 1 patterns: the
+    whole range of expf(d <= 0)), on NaNs, and both exact LSE flavours on 2^24 operand pairs: zero bit mismatches."""
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st = lib.rnnt_b200_debug_lse_selfcheck(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), p(bad))
+    torch.cuda.synchronize()
+    assert st == 0 and int(bad.item()) == 0

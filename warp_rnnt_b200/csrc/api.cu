@@ -148,6 +148,55 @@ static Pipeline *get_pipeline_locked() {
     return p;
 }
 
+// Self-check of the restated log1pf (common.cuh:log1pf_unit) against libdevice: every float in [+0, 1], a NaN, and the
+// complete exact LSE (both flavours) on pseudo-random operand pairs.  counts[0] += mismatches.
+__global__ void k_lse_selfcheck(unsigned long long *counts) {
+    unsigned long long bad = 0;
+    const uint32_t top = 0x3f800000u;                       // 1.0f
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= top; b += (uint64_t)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((uint32_t)b);
+        const uint32_t r0 = __float_as_uint(log1pf(x)), r1 = __float_as_uint(log1pf_unit(x));
+        bad += (r0 != r1);
+    }
+    // NaN in, NaN out (the guard lives in lse_tail); NaN / inf - inf operands of the whole LSE stay NaN like the reference's
+    { const float n = lse_tail(-1.0f, __uint_as_float(0x7fc00000u + threadIdx.x)); bad += !(n != n); }
+    {
+        const float qn = __uint_as_float(0x7fc00000u), inf = __uint_as_float(0x7f800000u);
+        const float A4[4] = {qn, 1.0f, -inf, inf}, B4[4] = {1.0f, qn, -inf, inf};
+        for (int k = 0; k < 4; ++k) {
+            const float a = A4[k], b2 = B4[k];
+            float mx, df;
+            if (a > b2) { mx = a; df = b2 - a; } else { mx = b2; df = a - b2; }
+            const float ref = mx + log1pf(expf(df)), got = lse<kExactDense>(a, b2);
+            bad += ((ref != ref) != (got != got)) || (ref == ref && __float_as_uint(ref) != __float_as_uint(got));
+            const float tmp = a - b2;
+            const float refc = (a == b2) ? (float)(a + M_LN2) : (tmp > 0) ? a + log1pf(expf(-tmp)) : (tmp <= 0) ? b2 + log1pf(expf(tmp)) : tmp;
+            const float gotc = lse<kExactCompact>(a, b2);
+            bad += ((refc != refc) != (gotc != gotc)) || (refc == refc && __float_as_uint(refc) != __float_as_uint(gotc));
+        }
+    }
+    // -0 as the larger operand: (-0) + log1p(e) and (+0) + log1p(e) are the same float for every e in [0, 1]
+    { const float r0 = lse<kExactDense>(-0.0f, -3.0f), r1 = -0.0f + log1pf(expf(-3.0f)); bad += (__float_as_uint(r0) != __float_as_uint(r1));
+      const float r2 = lse<kExactDense>(-0.0f, -__uint_as_float(0x7f800000u)), r3 = -0.0f + log1pf(0.0f); bad += (__float_as_uint(r2) != __float_as_uint(r3)); }
+    // the whole LSE on operand pairs spread over the magnitudes the lattices see (a hash of the thread index)
+    uint32_t h = 0x9e3779b9u * ((uint32_t)blockIdx.x * blockDim.x + threadIdx.x + 1u);
+    for (int k = 0; k < 64; ++k) {
+        h = h * 1664525u + 1013904223u;
+        const float a = -(float)(h >> 8) * (1.0f / 65536.0f) * 40.0f;       // [-10240, 0]
+        h = h * 1664525u + 1013904223u;
+        const float d = ((float)(h >> 8) * (1.0f / 16777216.0f) - 0.5f) * ((k & 1) ? 40.0f : 2.0f);
+        const float b2 = a + d;
+        float mx, df;
+        if (a > b2) { mx = a; df = b2 - a; } else { mx = b2; df = a - b2; }
+        const float ref = mx + log1pf(expf(df));
+        bad += (__float_as_uint(ref) != __float_as_uint(lse<kExactDense>(a, b2)));
+        const float tmp = a - b2;
+        float refc = (a == b2) ? (float)(a + M_LN2) : ((tmp > 0) ? a + log1pf(expf(-tmp)) : b2 + log1pf(expf(tmp)));
+        bad += (__float_as_uint(refc) != __float_as_uint(lse<kExactCompact>(a, b2)));
+    }
+    if (bad) atomicAdd(counts, bad);
+}
+
 #define RNNT_TRY(expr, code)                                            \
     do {                                                                \
         cudaError_t e__ = (expr);                                       \
@@ -283,6 +332,11 @@ uint64_t rnnt_b200_launch_count(void) { return g_launches.load(std::memory_order
 void rnnt_b200_debug_guard_poison(int n, float delta) {
     g_poison_delta.store(delta, std::memory_order_relaxed);
     g_poison_n.store(n, std::memory_order_relaxed);
+}
+int rnnt_b200_debug_lse_selfcheck(void *stream, unsigned long long *mismatches) {
+    if (!mismatches) return RNNT_STATUS_INVALID_ARGUMENT;
+    rnnt::k_lse_selfcheck<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(mismatches);
+    return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_WARP_FAILED;
 }
 void rnnt_b200_debug_fused_trace(void *buf) { rnnt::set_fused_trace(static_cast<long long *>(buf)); }
 
