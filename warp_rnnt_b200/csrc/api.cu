@@ -162,8 +162,8 @@ __global__ void k_lse_selfcheck(unsigned long long *counts) {
     { const float n = lse_tail(-1.0f, __uint_as_float(0x7fc00000u + threadIdx.x)); bad += !(n != n); }
     {
         const float qn = __uint_as_float(0x7fc00000u), inf = __uint_as_float(0x7f800000u);
-        const float A4[4] = {qn, 1.0f, -inf, inf}, B4[4] = {1.0f, qn, -inf, inf};
-        for (int k = 0; k < 4; ++k) {
+        const float A4[8] = {qn, 1.0f, -inf, inf, -3.0f, 0.0f, -inf, -2.5f}, B4[8] = {1.0f, qn, -inf, inf, -3.0f, -0.0f, -7.0f, -inf};
+        for (int k = 0; k < 8; ++k) {
             const float a = A4[k], b2 = B4[k];
             float mx, df;
             if (a > b2) { mx = a; df = b2 - a; } else { mx = b2; df = a - b2; }
