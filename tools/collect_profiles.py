@@ -32,6 +32,9 @@ def main():
         elif f == "tests.log":
             shutil.copy(src, os.path.join(P, r + "gpu_tests.log"))
             done.append(r + "gpu_tests.log")
+        elif f == "tests_quick.log":                # QUICK=1 pass on the final tree (default paths + fast LSE + smoke)
+            shutil.copy(src, os.path.join(P, r + "gpu_tests_final.log"))
+            done.append(r + "gpu_tests_final.log")
         elif f.startswith("launches_") and f.endswith(".csv"):
             rows = [x for x in csv.reader(open(src)) if len(x) > 5]
             if not rows:
